@@ -104,6 +104,12 @@ int smx_group_integral(const smx_group_desc* g, int64_t d_out, double* q, int ac
 /* barycentric.py:13-31 compute_weights on the device: w_j = prod_{i != j} 1 / (nodes_i - nodes_j). */
 int smx_compute_weights(const double* nodes, int64_t m, double* w, void* stream);
 
+/* barycentric.py:34-66 evaluate_basis_unnormalized (derivative = 0) and :126-155
+ * evaluate_basis_gradient_unnormalized (derivative = 1) for N points of one dimension:
+ * x (N), xi and w (m), degree nu  ->  out (N, m); columns beyond nu are zero. */
+int smx_basis(const double* x, int64_t N, const double* xi, const double* w, int64_t m, int64_t nu, int derivative,
+              double* out, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------------------- */
 typedef struct {
     int64_t d_in, d_out;

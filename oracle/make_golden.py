@@ -46,7 +46,8 @@ def split_ld(a):
 
 def layout_of(ip):
     """The six per-group arrays + offset of reference interpolation.py:230-235."""
-    out = {"offset": np.atleast_1d(np.asarray(getattr(ip, P + "offset"), dtype=np.float64))}
+    # the reference keeps a scalar 0 when zeta_0 == 0; store the broadcast (d_out,) form in every case
+    out = {"offset": np.array(np.broadcast_to(np.asarray(getattr(ip, P + "offset"), dtype=np.float64), (ip.d_out,)))}
     for n in getattr(ip, P + "n_2_F"):
         out[f"F_{n}"] = np.asarray(getattr(ip, P + "n_2_F")[n], dtype=np.float64)
         out[f"nodes_{n}"] = np.asarray(getattr(ip, P + "n_2_nodes")[n], dtype=np.float64)

@@ -18,8 +18,8 @@ ROOT = PKG.parent
 HOST_LIB = PKG / "libsmolyax_host.so"
 CUDA_LIB = PKG / "libsmolyax_b200.so"
 
-HOST_SOURCES = ["smx_host.cpp"]
-CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu"]
+HOST_SOURCES = ["smx_host.cpp", "smx_plan.cpp"]
+CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu", "smx_plan.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -39,11 +39,11 @@ def _run(cmd):
 
 def build_host(force: bool = False) -> Path:
     srcs = [CSRC / s for s in HOST_SOURCES]
-    if not force and _newer(HOST_LIB, srcs):
+    if not force and _newer(HOST_LIB, srcs + sorted(CSRC.glob("*.h"))):
         return HOST_LIB
     cxx = os.environ.get("CXX", "g++")
     tmp = HOST_LIB.with_suffix(f".so.tmp{os.getpid()}")
-    _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", *srcs, "-o", tmp])
+    _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread", *srcs, "-o", tmp])
     os.replace(tmp, HOST_LIB)
     return HOST_LIB
 
@@ -54,22 +54,36 @@ def nvcc_path():
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every translation unit for sm_100a (objects in csrc/.build, in parallel) and link the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs = [CSRC / s for s in CUDA_SOURCES]
-    deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "smolyax_b200.h"]
-    if not force and _newer(CUDA_LIB, deps):
+    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "smolyax_b200.h"]
+    if not force and _newer(CUDA_LIB, srcs + headers):
         return CUDA_LIB
     nvcc = nvcc_path()
     if nvcc is None:
-        raise RuntimeError("nvcc not found: cannot build libsmolyax_b200.so (sm_100a)")
-    tmp = CUDA_LIB.with_suffix(f".so.tmp{os.getpid()}")
-    cmd = [nvcc, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-           "-Xcompiler", "-fno-fast-math", "--fmad=true", "-I", ROOT / "include", "-I", CSRC, *srcs, "-o", tmp]
+        raise RuntimeError("nvcc not found: cannot build libsmolyax_b200.so (sm_100a); there is no CPU fallback")
+    objdir = CSRC / ".build"
+    objdir.mkdir(exist_ok=True)
+    common = [nvcc, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
+              "--fmad=true", "-I", ROOT / "include", "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    out = _run(cmd)
+        common += ["-Xptxas", "-v"]
+
+    def compile_one(src: Path):
+        obj = objdir / (src.name + ".o")
+        if not force and _newer(obj, [src] + headers):
+            return obj, ""
+        return obj, _run([*common, "-c", src, "-o", obj])
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    tmp = CUDA_LIB.with_suffix(f".so.tmp{os.getpid()}")
+    _run([nvcc, *NVCC_ARCH, "-shared", *[obj for obj, _ in results], "-o", tmp])
     os.replace(tmp, CUDA_LIB)
     if verbose:
-        print(out)
+        print("".join(out for _, out in results))
     return CUDA_LIB
 
 

@@ -1,0 +1,146 @@
+"""ctypes binding of libsmolyax_b200.so (the C-ABI of include/smolyax_b200.h).
+
+The library is the only compute path of this package.  If it cannot be loaded (and cannot be built because nvcc is
+absent) importing this module raises: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_void_p
+
+import numpy as np
+
+from . import _build
+
+SMX_KEEP_GROUPS = 1
+SMX_NO_FAST_PATH = 2
+
+_STATUS = {1: "invalid argument", 2: "CUDA error", 3: "out of device memory", 4: "unsupported shape", 5: "no sm_100 device"}
+
+
+class SmolyaxCudaError(RuntimeError):
+    pass
+
+
+class GroupDesc(ctypes.Structure):
+    _fields_ = [
+        ("n", c_int32),
+        ("nn", c_int64),
+        ("tau", c_void_p),
+        ("F", c_void_p),
+        ("nodes", c_void_p),
+        ("weights", c_void_p),
+        ("dims", c_void_p),
+        ("degs", c_void_p),
+        ("zetas", c_void_p),
+        ("quad", c_void_p),
+    ]
+
+
+class InterpDesc(ctypes.Structure):
+    _fields_ = [
+        ("d_in", c_int64),
+        ("d_out", c_int64),
+        ("offset", c_void_p),
+        ("n_groups", c_int32),
+        ("groups", POINTER(GroupDesc)),
+        ("flags", c_uint32),
+    ]
+
+
+class Info(ctypes.Structure):
+    _fields_ = [(name, c_int64) for name in (
+        "d_in", "d_out", "n_summands", "w_raw", "w_pad", "n_terms", "n_entries", "n_rows", "n_chunks", "padded_fma",
+        "device_bytes")] + [(name, c_int32) for name in ("has_fast_path", "has_groups", "nested")]
+
+
+EXPORTS = {
+    "smx_create": (c_int, [POINTER(InterpDesc), c_int, POINTER(c_void_p)]),
+    "smx_destroy": (c_int, [c_void_p]),
+    "smx_eval": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "smx_gradient": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "smx_integral": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "smx_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64]),
+    "smx_group_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
+    "smx_group_gradient": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
+    "smx_group_integral": (c_int, [POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
+    "smx_compute_weights": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "smx_basis": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "smx_get_info": (c_int, [c_void_p, POINTER(Info)]),
+    "smx_launch_count": (c_int64, []),
+    "smx_last_error": (c_char_p, []),
+    "smx_version": (c_int, []),
+    "smx_arch": (c_char_p, []),
+}
+
+
+def _load():
+    path = _build.CUDA_LIB
+    if not path.exists():
+        path = _build.build_cuda()  # raises if nvcc is missing: no CPU fallback
+    lib = ctypes.CDLL(str(path))
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
+        fn.restype, fn.argtypes = restype, argtypes
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int, where: str = ""):
+    if status != 0:
+        msg = lib.smx_last_error().decode(errors="replace")
+        text = f"{where}: {_STATUS.get(status, status)}: {msg}"
+        if status == 1:
+            raise AssertionError(text)  # the reference signals bad inputs with assert
+        raise SmolyaxCudaError(text)
+
+
+def group_sizes(layout):
+    return sorted(int(key.split("_")[1]) for key in layout if key.startswith("zetas_"))
+
+
+def pack_groups(layout, ptr_of):
+    """Build the smx_group_desc array for a reference-layout dict.  ``ptr_of(array, dtype)`` returns
+    ``(keepalive, address)`` — host arrays for smx_create, device tensors for the seam twins."""
+    ns = group_sizes(layout)
+    arr = (GroupDesc * max(len(ns), 1))()
+    keep = []
+    for i, n in enumerate(ns):
+        F = layout[f"F_{n}"]
+        tau = np.ascontiguousarray(np.asarray(F.shape[2:], dtype=np.int64) - 1)
+        keep.append(tau)
+        arr[i].n, arr[i].nn, arr[i].tau = n, F.shape[0], tau.ctypes.data
+        for field, key, dt in (("F", "F", np.float64), ("nodes", "nodes", np.float64), ("weights", "weights", np.float64),
+                               ("dims", "dims", np.int64), ("degs", "degs", np.int64), ("zetas", "zetas", np.int64),
+                               ("quad", "quad", np.float64)):
+            a = layout.get(f"{key}_{n}")
+            if a is None:
+                setattr(arr[i], field, None)
+                continue
+            k, addr = ptr_of(a, dt)
+            keep.append(k)
+            setattr(arr[i], field, addr)
+    return arr, len(ns), keep
+
+
+def host_ptr(a, dt):
+    a = np.ascontiguousarray(a, dtype=dt)
+    return a, a.ctypes.data
+
+
+def create(layout, d_in: int, d_out: int, flags: int, device: int = -1):
+    arr, n_groups, keep = pack_groups(layout, host_ptr)
+    off = np.ascontiguousarray(np.broadcast_to(np.asarray(layout["offset"], dtype=np.float64), (d_out,)))
+    desc = InterpDesc(d_in, d_out, off.ctypes.data, n_groups, arr, flags)
+    handle = c_void_p()
+    check(lib.smx_create(ctypes.byref(desc), device, ctypes.byref(handle)), "smx_create")
+    del keep
+    return handle
+
+
+def info(handle) -> dict:
+    out = Info()
+    check(lib.smx_get_info(handle, ctypes.byref(out)), "smx_get_info")
+    return {name: int(getattr(out, name)) for name, _ in Info._fields_}

@@ -1,0 +1,352 @@
+// C-ABI of include/smolyax_b200.h: handle life cycle, dispatch to the kernels, host-buffer pipeline.
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "smx_common.cuh"
+
+namespace smx {
+
+static thread_local std::string t_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(int status, const std::string& msg) {
+    t_error = msg;
+    return status;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    t_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? SMX_ERR_OUT_OF_MEMORY : SMX_ERR_CUDA;
+}
+
+}  // namespace smx
+
+using namespace smx;
+
+struct smx_interp {
+    int device = 0;
+    int64_t d_in = 0, d_out = 0;
+    smx_info info{};
+    bool has_fast = false, has_groups = false;
+    FastDevice fast;
+    std::vector<SeamGroup> groups;
+    std::vector<void*> owned;  // device allocations behind `groups`
+    double* d_offset = nullptr;
+    double* integral_ws = nullptr;
+    int64_t integral_ws_doubles = 0;
+    // host pipeline (lazy)
+    static constexpr int kStages = 3;
+    cudaStream_t streams[kStages] = {nullptr, nullptr, nullptr};
+    double* stage_x[kStages] = {nullptr, nullptr, nullptr};
+    double* stage_y[kStages] = {nullptr, nullptr, nullptr};
+    int64_t stage_points = 0;
+    std::mutex host_mutex;
+};
+
+namespace {
+
+template <class T>
+int upload_array(smx_interp* h, const T* host, size_t count, const T** out) {
+    *out = nullptr;
+    if (count == 0 || host == nullptr) return SMX_OK;
+    void* d = nullptr;
+    SMX_CUDA(cudaMalloc(&d, count * sizeof(T)));
+    h->owned.push_back(d);
+    h->info.device_bytes += (int64_t)(count * sizeof(T));
+    SMX_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(d);
+    return SMX_OK;
+}
+
+int check_device(int device, int* resolved) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(SMX_ERR_NO_DEVICE, "no CUDA device visible: smolyax_b200 has no CPU fallback");
+    }
+    if (device < 0) SMX_CUDA(cudaGetDevice(&device));
+    if (device >= count) return fail(SMX_ERR_INVALID_ARG, "device ordinal out of range");
+    SMX_CUDA(cudaSetDevice(device));
+    int major = 0;
+    SMX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(SMX_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only");
+    *resolved = device;
+    return SMX_OK;
+}
+
+void release(smx_interp* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    fast_free(h->fast);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->d_offset) cudaFree(h->d_offset);
+    if (h->integral_ws) cudaFree(h->integral_ws);
+    for (int i = 0; i < smx_interp::kStages; ++i) {
+        if (h->stage_x[i]) cudaFree(h->stage_x[i]);
+        if (h->stage_y[i]) cudaFree(h->stage_y[i]);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    delete h;
+}
+
+int ensure_stages(smx_interp* h, int64_t points, int64_t ldx) {
+    if (h->stage_points >= points && h->stage_x[0]) return SMX_OK;
+    for (int i = 0; i < smx_interp::kStages; ++i) {
+        if (h->stage_x[i]) cudaFree(h->stage_x[i]);
+        if (h->stage_y[i]) cudaFree(h->stage_y[i]);
+        h->stage_x[i] = h->stage_y[i] = nullptr;
+        if (!h->streams[i]) SMX_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+        SMX_CUDA(cudaMalloc((void**)&h->stage_x[i], (size_t)points * h->d_in * sizeof(double)));
+        SMX_CUDA(cudaMalloc((void**)&h->stage_y[i], (size_t)points * h->d_out * sizeof(double)));
+    }
+    (void)ldx;
+    h->stage_points = points;
+    return SMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
+    if (!desc || !out) return fail(SMX_ERR_INVALID_ARG, "smx_create: null argument");
+    *out = nullptr;
+    if (desc->d_in <= 0 || desc->d_out <= 0) return fail(SMX_ERR_INVALID_ARG, "smx_create: d_in and d_out must be positive");
+    if (desc->n_groups < 0 || (desc->n_groups > 0 && !desc->groups)) return fail(SMX_ERR_INVALID_ARG, "smx_create: bad group list");
+    int dev = 0, rc;
+    if ((rc = check_device(device, &dev))) return rc;
+
+    std::unique_ptr<smx_interp, void (*)(smx_interp*)> h(new smx_interp(), release);
+    h->device = dev;
+    h->d_in = desc->d_in;
+    h->d_out = desc->d_out;
+    h->info.d_in = desc->d_in;
+    h->info.d_out = desc->d_out;
+
+    std::vector<GroupView> views;
+    for (int32_t g = 0; g < desc->n_groups; ++g) {
+        const smx_group_desc& d = desc->groups[g];
+        if (d.n < 1 || !d.tau || d.nn < 0) return fail(SMX_ERR_INVALID_ARG, "smx_create: malformed group descriptor");
+        GroupView v;
+        v.n = d.n;
+        v.nn = d.nn;
+        v.tau.assign(d.tau, d.tau + d.n);
+        v.F = d.F;
+        v.nodes = d.nodes;
+        v.weights = d.weights;
+        v.dims = d.dims;
+        v.degs = d.degs;
+        v.zetas = d.zetas;
+        v.quad = d.quad;
+        views.push_back(v);
+    }
+
+    bool want_fast = !(desc->flags & SMX_NO_FAST_PATH);
+    bool want_groups = (desc->flags & SMX_KEEP_GROUPS) != 0 || !want_fast;
+    if (want_fast) {
+        FastPlan plan;
+        const std::string err = build_fast_plan(desc->d_in, desc->d_out, desc->offset, views, plan);
+        if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create: " + err);
+        h->info.n_summands = plan.n_summands;
+        h->info.w_raw = plan.w_raw;
+        h->info.w_pad = plan.w_pad;
+        h->info.n_terms = plan.n_terms;
+        h->info.n_entries = plan.n_entries;
+        h->info.n_rows = plan.n_rows;
+        h->info.n_chunks = plan.n_chunks;
+        h->info.padded_fma = plan.padded_fma;
+        h->info.nested = plan.nested ? 1 : 0;
+        rc = fast_upload(plan, h->fast);
+        if (rc == SMX_ERR_UNSUPPORTED) {
+            fast_free(h->fast);  // fall back to the per-summand kernels; still a CUDA path
+            want_groups = true;
+        } else if (rc) {
+            return rc;
+        } else {
+            h->has_fast = true;
+            h->info.device_bytes += h->fast.bytes;
+        }
+    }
+    if (want_groups) {
+        for (size_t gi = 0; gi < views.size(); ++gi) {
+            const smx_group_desc& d = desc->groups[gi];
+            const GroupView& v = views[gi];
+            if (d.n > kSeamMaxN) return fail(SMX_ERR_UNSUPPORTED, "smx_create: more than 8 active dimensions per summand");
+            smx_group_desc dd = d;
+            const size_t slots = (size_t)d.nn * d.n, tw = (size_t)v.tw();
+            if ((rc = upload_array(h.get(), d.F, (size_t)d.nn * desc->d_out * v.fsize(), &dd.F))) return rc;
+            if ((rc = upload_array(h.get(), d.nodes, slots * tw, &dd.nodes))) return rc;
+            if ((rc = upload_array(h.get(), d.weights, slots * tw, &dd.weights))) return rc;
+            if ((rc = upload_array(h.get(), d.dims, slots, &dd.dims))) return rc;
+            if ((rc = upload_array(h.get(), d.degs, slots, &dd.degs))) return rc;
+            if ((rc = upload_array(h.get(), d.zetas, (size_t)d.nn, &dd.zetas))) return rc;
+            if ((rc = upload_array(h.get(), d.quad, slots * tw, &dd.quad))) return rc;
+            SeamGroup sg;
+            if ((rc = make_seam_group(&dd, sg))) return rc;
+            h->groups.push_back(sg);
+            h->integral_ws_doubles = std::max(h->integral_ws_doubles, seam_integral_workspace(sg, desc->d_out));
+            if (!want_fast) {
+                h->info.n_summands += d.nn;
+                h->info.w_pad += d.nn * v.fsize();
+            }
+        }
+        h->has_groups = true;
+    }
+    {
+        std::vector<double> off((size_t)desc->d_out, 0.0);
+        if (desc->offset) std::memcpy(off.data(), desc->offset, sizeof(double) * desc->d_out);
+        SMX_CUDA(cudaMalloc((void**)&h->d_offset, sizeof(double) * desc->d_out));
+        SMX_CUDA(cudaMemcpy(h->d_offset, off.data(), sizeof(double) * desc->d_out, cudaMemcpyHostToDevice));
+        h->info.device_bytes += (int64_t)sizeof(double) * desc->d_out;
+    }
+    h->info.has_fast_path = h->has_fast;
+    h->info.has_groups = h->has_groups;
+    *out = h.release();
+    return SMX_OK;
+}
+
+int smx_destroy(smx_interp* h) {
+    release(h);
+    return SMX_OK;
+}
+
+int smx_get_info(const smx_interp* h, smx_info* info) {
+    if (!h || !info) return fail(SMX_ERR_INVALID_ARG, "smx_get_info: null argument");
+    *info = h->info;
+    return SMX_OK;
+}
+
+int smx_eval(smx_interp* h, const double* x, int64_t N, int64_t ldx, double* y, void* stream) {
+    if (!h || N < 0) return fail(SMX_ERR_INVALID_ARG, "smx_eval: bad arguments");
+    if (N == 0) return SMX_OK;
+    if (!x || !y || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_eval: null buffer or ldx < d_in");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->has_fast) return fast_eval(h->fast, x, N, ldx, y, st);
+    int rc;
+    if ((rc = fill_rows(y, N, h->d_out, h->d_offset, st))) return rc;
+    for (const SeamGroup& g : h->groups)
+        if ((rc = seam_eval(x, N, ldx, g, h->d_out, y, st))) return rc;
+    return SMX_OK;
+}
+
+int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double* J, void* stream) {
+    if (!h || N < 0) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: bad arguments");
+    if (N == 0) return SMX_OK;
+    if (!x || !J || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: null buffer or ldx < d_in");
+    if (!h->has_groups && h->info.n_summands > 0)
+        return fail(SMX_ERR_INVALID_ARG, "smx_gradient: handle was created without SMX_KEEP_GROUPS");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * h->d_out * h->d_in, st));
+    int rc;
+    for (const SeamGroup& g : h->groups)
+        if ((rc = seam_gradient(x, N, ldx, h->d_in, g, h->d_out, J, st))) return rc;
+    return SMX_OK;
+}
+
+int smx_integral(smx_interp* h, double* q, void* stream) {
+    if (!h || !q) return fail(SMX_ERR_INVALID_ARG, "smx_integral: null argument");
+    if (!h->has_groups && h->info.n_summands > 0)
+        return fail(SMX_ERR_INVALID_ARG, "smx_integral: handle was created without SMX_KEEP_GROUPS");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = fill_rows(q, 1, h->d_out, h->d_offset, st))) return rc;
+    if (h->integral_ws_doubles > 0 && !h->integral_ws) {
+        SMX_CUDA(cudaMalloc((void**)&h->integral_ws, sizeof(double) * h->integral_ws_doubles));
+        h->info.device_bytes += (int64_t)sizeof(double) * h->integral_ws_doubles;
+    }
+    for (const SeamGroup& g : h->groups)
+        if ((rc = seam_integral(g, h->d_out, q, h->integral_ws, h->integral_ws_doubles, st))) return rc;
+    return SMX_OK;
+}
+
+int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, double* y_host, int64_t chunk_points) {
+    if (!h || N < 0) return fail(SMX_ERR_INVALID_ARG, "smx_eval_host: bad arguments");
+    if (N == 0) return SMX_OK;
+    if (!x_host || !y_host || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_eval_host: null buffer or ldx < d_in");
+    std::lock_guard<std::mutex> lock(h->host_mutex);
+    SMX_CUDA(cudaSetDevice(h->device));
+    if (chunk_points <= 0) {
+        // ~64 MiB of x per stage keeps the copy engines and the SMs busy at the same time
+        chunk_points = std::max<int64_t>(1024, (64ll << 20) / (int64_t)(h->d_in * sizeof(double)));
+    }
+    chunk_points = std::min(chunk_points, N);
+    int rc;
+    if ((rc = ensure_stages(h, chunk_points, ldx))) return rc;
+    int64_t done = 0;
+    for (int64_t c = 0; done < N; ++c, done += chunk_points) {
+        const int s = (int)(c % smx_interp::kStages);
+        const int64_t n = std::min(chunk_points, N - done);
+        cudaStream_t st = h->streams[s];
+        // stream order protects the stage buffers: the next use of stage s is queued behind this one
+        SMX_CUDA(cudaMemcpy2DAsync(h->stage_x[s], sizeof(double) * h->d_in, x_host + done * ldx, sizeof(double) * ldx,
+                                   sizeof(double) * h->d_in, (size_t)n, cudaMemcpyHostToDevice, st));
+        if ((rc = smx_eval(h, h->stage_x[s], n, h->d_in, h->stage_y[s], st))) return rc;
+        SMX_CUDA(cudaMemcpyAsync(y_host + done * h->d_out, h->stage_y[s], sizeof(double) * (size_t)n * h->d_out,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < smx_interp::kStages; ++s) SMX_CUDA(cudaStreamSynchronize(h->streams[s]));
+    return SMX_OK;
+}
+
+int smx_group_eval(const double* x, int64_t N, int64_t ldx, int64_t d_in, const smx_group_desc* g, int64_t d_out,
+                   double* y, int accumulate, void* stream) {
+    if (N < 0 || d_out <= 0 || ldx < d_in) return fail(SMX_ERR_INVALID_ARG, "smx_group_eval: bad sizes");
+    if (N == 0) return SMX_OK;
+    if (!x || !y) return fail(SMX_ERR_INVALID_ARG, "smx_group_eval: null buffer");
+    SeamGroup sg;
+    int rc;
+    if ((rc = make_seam_group(g, sg))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!accumulate && (rc = fill_rows(y, N, d_out, nullptr, st))) return rc;
+    return seam_eval(x, N, ldx, sg, d_out, y, st);
+}
+
+int smx_group_gradient(const double* x, int64_t N, int64_t ldx, int64_t d_in, const smx_group_desc* g, int64_t d_out,
+                       double* J, int accumulate, void* stream) {
+    if (N < 0 || d_out <= 0 || ldx < d_in) return fail(SMX_ERR_INVALID_ARG, "smx_group_gradient: bad sizes");
+    if (N == 0) return SMX_OK;
+    if (!x || !J) return fail(SMX_ERR_INVALID_ARG, "smx_group_gradient: null buffer");
+    SeamGroup sg;
+    int rc;
+    if ((rc = make_seam_group(g, sg))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!accumulate) SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * d_out * d_in, st));
+    return seam_gradient(x, N, ldx, d_in, sg, d_out, J, st);
+}
+
+int smx_group_integral(const smx_group_desc* g, int64_t d_out, double* q, int accumulate, void* stream) {
+    if (d_out <= 0 || !q) return fail(SMX_ERR_INVALID_ARG, "smx_group_integral: bad arguments");
+    SeamGroup sg;
+    int rc;
+    if ((rc = make_seam_group(g, sg))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!accumulate && (rc = fill_rows(q, 1, d_out, nullptr, st))) return rc;
+    const int64_t ws = seam_integral_workspace(sg, d_out);
+    double* work = nullptr;
+    SMX_CUDA(cudaMallocAsync((void**)&work, sizeof(double) * ws, st));
+    rc = seam_integral(sg, d_out, q, work, ws, st);
+    cudaFreeAsync(work, st);
+    return rc;
+}
+
+int smx_compute_weights(const double* nodes, int64_t m, double* w, void* stream) {
+    if (m < 0 || (m > 0 && (!nodes || !w))) return fail(SMX_ERR_INVALID_ARG, "smx_compute_weights: bad arguments");
+    return device_compute_weights(nodes, m, w, static_cast<cudaStream_t>(stream));
+}
+
+int smx_basis(const double* x, int64_t N, const double* xi, const double* w, int64_t m, int64_t nu, int derivative,
+              double* out, void* stream) {
+    if (N < 0 || m < 0 || (N > 0 && m > 0 && (!x || !xi || !w || !out)))
+        return fail(SMX_ERR_INVALID_ARG, "smx_basis: bad arguments");
+    return device_basis(x, N, xi, w, m, nu, derivative, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t smx_launch_count(void) { return g_launches.load(); }
+const char* smx_last_error(void) { return t_error.c_str(); }
+int smx_version(void) { return 1; }
+const char* smx_arch(void) { return "sm_100a"; }
+
+}  // extern "C"

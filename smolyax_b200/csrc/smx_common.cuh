@@ -1,0 +1,96 @@
+// Shared declarations of the CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "smolyax_b200.h"
+#include "smx_plan.h"
+
+namespace smx {
+
+// ---- error reporting: thread-local message, status codes of smolyax_b200.h -------------------------------------
+void set_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+extern std::atomic<int64_t> g_launches;
+
+#define SMX_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return smx::cuda_fail(e__, #call); \
+    } while (0)
+
+#define SMX_LAUNCH_CHECK(name)                                \
+    do {                                                      \
+        smx::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return smx::cuda_fail(e__, name); \
+    } while (0)
+
+constexpr int kSeamMaxN = 8;  // active dimensions per summand supported by the per-summand kernels
+
+// Device-side view of one reference-layout group (all pointers are device pointers).
+struct SeamGroup {
+    int n;
+    long long nn;
+    int shape[kSeamMaxN];        // tau_j + 1
+    long long fstride[kSeamMaxN];  // element stride of axis j inside one (summand, output) block of F
+    long long fsize;             // prod shape
+    int tw;                      // taumax + 1
+    int ent_off[kSeamMaxN];      // prefix sums of shape: slot j's basis occupies rows [ent_off[j], ent_off[j+1])
+    int ent_total;
+    const double* F;
+    const double* nodes;
+    const double* weights;
+    const long long* dims;
+    const long long* degs;
+    const long long* zetas;
+    const double* quad;
+};
+
+int make_seam_group(const smx_group_desc* g, SeamGroup& out);
+
+// per-summand kernels on the reference layout (smx_seam.cu)
+int seam_eval(const double* x, int64_t N, int64_t ldx, const SeamGroup& g, int64_t d_out, double* y, cudaStream_t st);
+int seam_gradient(const double* x, int64_t N, int64_t ldx, int64_t d_in, const SeamGroup& g, int64_t d_out, double* J,
+                  cudaStream_t st);
+int seam_integral(const SeamGroup& g, int64_t d_out, double* q, double* workspace, int64_t workspace_doubles,
+                  cudaStream_t st);
+int64_t seam_integral_workspace(const SeamGroup& g, int64_t d_out);
+int fill_rows(double* y, int64_t N, int64_t d_out, const double* row, cudaStream_t st);  // y[p,:] = row (or 0)
+int device_compute_weights(const double* nodes, int64_t m, double* w, cudaStream_t st);
+int device_basis(const double* x, int64_t N, const double* xi, const double* w, int64_t m, int64_t nu, int derivative,
+                 double* out, cudaStream_t st);
+
+// fast path (smx_fast.cu)
+struct FastDevice {
+    int64_t d_in = 0, d_out = 0;
+    int32_t n_entries_padded = 0, n_rows = 0, n_levels = 0, n_hot = 0, n_chunks = 0;
+    int32_t level_off[kMaxLevels + 2] = {0};
+    int32_t* ent_dim = nullptr;
+    int32_t* ent_deg = nullptr;
+    int32_t* ent_eta = nullptr;
+    double* eta = nullptr;
+    int32_t* row_parent = nullptr;
+    int32_t* row_hslot = nullptr;
+    int32_t* hot_dim = nullptr;
+    int32_t* hot_deg = nullptr;
+    int32_t* hot_eta = nullptr;
+    int32_t* chunk_block = nullptr;
+    int32_t* chunk_off = nullptr;
+    int32_t* chunk_rows = nullptr;
+    double* coef = nullptr;
+    double* c0 = nullptr;
+    int max_ent_deg = 0;
+    int64_t bytes = 0;
+    int sm_count = 148;
+};
+int fast_upload(const FastPlan& plan, FastDevice& dev);
+void fast_free(FastDevice& dev);
+int fast_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
+
+}  // namespace smx

@@ -1,0 +1,532 @@
+// Plan compiler: reference per-group layout -> hierarchical block-sparse device layout (see smx_plan.h).
+// Host-only C++ (long double arithmetic); compiled into both libsmolyax_host.so and libsmolyax_b200.so.
+#include "smx_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <thread>
+#include <unordered_map>
+
+namespace smx {
+namespace {
+
+typedef long double ld;
+typedef std::vector<int64_t> Key;  // sorted codes dim * kCode + deg
+constexpr int64_t kCode = 65536;
+
+struct KeyHash {
+    size_t operator()(const Key& k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (int64_t v : k) {
+            h ^= (uint64_t)v;
+            h *= 1099511628211ull;
+        }
+        return (size_t)h;
+    }
+};
+
+struct PairInfo {
+    int dim, deg;
+    const double* nodes;   // deg+1 nodes of this (dim, deg), as stored in the layout
+    std::vector<ld> minv;  // (deg+1)^2: Newton coefficient k = sum_m minv[k*(deg+1)+m] * value_m
+};
+
+// Gauss-Jordan inverse with partial pivoting in long double.
+bool invert(std::vector<ld> a, int n, std::vector<ld>& inv) {
+    inv.assign((size_t)n * n, 0.0L);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0L;
+    for (int c = 0; c < n; ++c) {
+        int p = c;
+        for (int r = c + 1; r < n; ++r)
+            if (fabsl(a[(size_t)r * n + c]) > fabsl(a[(size_t)p * n + c])) p = r;
+        if (a[(size_t)p * n + c] == 0.0L || !std::isfinite((double)a[(size_t)p * n + c])) return false;
+        if (p != c)
+            for (int j = 0; j < n; ++j) {
+                std::swap(a[(size_t)p * n + j], a[(size_t)c * n + j]);
+                std::swap(inv[(size_t)p * n + j], inv[(size_t)c * n + j]);
+            }
+        const ld d = 1.0L / a[(size_t)c * n + c];
+        for (int j = 0; j < n; ++j) {
+            a[(size_t)c * n + j] *= d;
+            inv[(size_t)c * n + j] *= d;
+        }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const ld f = a[(size_t)r * n + c];
+            if (f == 0.0L) continue;
+            for (int j = 0; j < n; ++j) {
+                a[(size_t)r * n + j] -= f * a[(size_t)c * n + j];
+                inv[(size_t)r * n + j] -= f * inv[(size_t)c * n + j];
+            }
+        }
+    }
+    return true;
+}
+
+// Greedy Leja ordering: start next to the centroid, then maximise the product of distances to the chosen ones.
+std::vector<double> leja_order(const double* pts, int n) {
+    std::vector<double> rest(pts, pts + n), out;
+    double mean = 0;
+    for (double v : rest) mean += v / n;
+    size_t best = 0;
+    for (size_t i = 1; i < rest.size(); ++i)
+        if (std::fabs(rest[i] - mean) < std::fabs(rest[best] - mean)) best = i;
+    out.push_back(rest[best]);
+    rest.erase(rest.begin() + best);
+    while (!rest.empty()) {
+        best = 0;
+        ld bestv = -1;
+        for (size_t i = 0; i < rest.size(); ++i) {
+            ld prod = 1;
+            for (double c : out) prod *= fabsl((ld)rest[i] - (ld)c);
+            if (prod > bestv) {
+                bestv = prod;
+                best = i;
+            }
+        }
+        out.push_back(rest[best]);
+        rest.erase(rest.begin() + best);
+    }
+    return out;
+}
+
+struct Summand {
+    int group;
+    int64_t s;
+    int n;
+    int64_t zeta;
+    int64_t mu_off;  // offset into mu_terms
+    int64_t count;   // prod (deg+1)
+};
+
+}  // namespace
+
+std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
+                            FastPlan& plan) {
+    plan = FastPlan();
+    plan.d_in = d_in;
+    plan.d_out = d_out;
+    if (d_in <= 0 || d_out <= 0) return "d_in and d_out must be positive";
+
+    // ---- 1. unique (dim, deg) pairs, per-dimension maximal degree ------------------------------------------
+    std::map<std::pair<int, int>, int> pair_id;
+    std::vector<PairInfo> pairs;
+    std::vector<int> maxdeg((size_t)d_in, 0);
+    std::vector<Summand> summands;
+    int64_t total_mu = 0;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const GroupView& G = groups[g];
+        if (G.n <= 0 || G.n > kMaxLevels) return "group with unsupported number of active dimensions";
+        if ((int)G.tau.size() != G.n) return "tau has wrong length";
+        if (!G.F || !G.nodes || !G.dims || !G.degs || !G.zetas) return "group descriptor has null arrays";
+        const int64_t tw = G.tw();
+        plan.w_pad += G.nn * G.fsize();
+        for (int64_t s = 0; s < G.nn; ++s) {
+            Summand sm{(int)g, s, G.n, G.zetas[s], total_mu, 1};
+            for (int j = 0; j < G.n; ++j) {
+                const int64_t dim = G.dims[s * G.n + j], deg = G.degs[s * G.n + j];
+                if (dim < 0 || dim >= d_in) return "sorted_dims entry out of range";
+                if (deg < 1 || deg > G.tau[j] || deg >= kCode) return "sorted_degs entry out of range";
+                for (int i = 0; i < j; ++i)
+                    if (G.dims[s * G.n + i] == dim) return "duplicate dimension inside one summand";
+                auto key = std::make_pair((int)dim, (int)deg);
+                if (!pair_id.count(key)) {
+                    pair_id[key] = (int)pairs.size();
+                    pairs.push_back({(int)dim, (int)deg, G.nodes + (s * G.n + j) * tw, {}});
+                }
+                maxdeg[dim] = std::max(maxdeg[dim], (int)deg);
+                sm.count *= (deg + 1);
+            }
+            total_mu += sm.count;
+            summands.push_back(sm);
+        }
+    }
+    plan.n_summands = (int64_t)summands.size();
+    plan.w_raw = total_mu;
+
+    // ---- 2. nestedness and Newton centres per dimension ---------------------------------------------------
+    std::vector<int32_t> eta_off((size_t)d_in + 1, 0);
+    for (int64_t d = 0; d < d_in; ++d) eta_off[d + 1] = eta_off[d] + maxdeg[d];
+    plan.eta.assign((size_t)eta_off[d_in], 0.0);
+    bool nested = true;
+    for (const PairInfo& p : pairs) {
+        const PairInfo& top = pairs[pair_id[{p.dim, maxdeg[p.dim]}]];
+        if (std::memcmp(p.nodes, top.nodes, sizeof(double) * (p.deg + 1)) != 0) nested = false;
+    }
+    plan.nested = nested;
+    for (int64_t d = 0; d < d_in; ++d) {
+        if (maxdeg[d] == 0) continue;
+        const PairInfo& top = pairs[pair_id[{(int)d, maxdeg[d]}]];
+        if (nested) {
+            std::copy(top.nodes, top.nodes + maxdeg[d], plan.eta.begin() + eta_off[d]);
+        } else {
+            std::vector<double> ord = leja_order(top.nodes, maxdeg[d] + 1);
+            std::copy(ord.begin(), ord.begin() + maxdeg[d], plan.eta.begin() + eta_off[d]);
+        }
+    }
+
+    // ---- 3. nodal values -> Newton coefficients, per pair -------------------------------------------------
+    for (PairInfo& p : pairs) {
+        const int m = p.deg + 1;
+        std::vector<ld> A((size_t)m * m);
+        const double* eta = plan.eta.data() + eta_off[p.dim];
+        for (int r = 0; r < m; ++r) {
+            ld v = 1.0L;
+            for (int k = 0; k < m; ++k) {
+                A[(size_t)r * m + k] = v;  // pi_k(xi_r)
+                if (k + 1 < m) v *= ((ld)p.nodes[r] - (ld)eta[k]);
+            }
+        }
+        if (!invert(A, m, p.minv)) return "interpolation nodes of one slot are not distinct";
+    }
+
+    // ---- 4. enumerate terms: every mu <= nu of every summand ------------------------------------------------
+    std::unordered_map<Key, int32_t, KeyHash> term_id;
+    std::vector<Key> term_key;
+    term_id.reserve((size_t)total_mu);
+    term_id[Key()] = 0;
+    term_key.push_back(Key());
+    std::vector<int32_t> mu_terms((size_t)total_mu);
+    {
+        Key key;
+        std::vector<std::pair<int64_t, int>> act;
+        for (const Summand& sm : summands) {
+            const GroupView& G = groups[sm.group];
+            int mu[kMaxLevels] = {0};
+            for (int64_t idx = 0; idx < sm.count; ++idx) {
+                act.clear();
+                for (int j = 0; j < sm.n; ++j)
+                    if (mu[j] > 0) act.push_back({G.dims[sm.s * sm.n + j], mu[j]});
+                std::sort(act.begin(), act.end());
+                key.clear();
+                for (auto& a : act) key.push_back(a.first * kCode + a.second);
+                auto it = term_id.find(key);
+                int32_t id;
+                if (it == term_id.end()) {
+                    id = (int32_t)term_key.size();
+                    term_id.emplace(key, id);
+                    term_key.push_back(key);
+                } else {
+                    id = it->second;
+                }
+                mu_terms[(size_t)(sm.mu_off + idx)] = id;
+                for (int j = sm.n - 1; j >= 0; --j) {  // odometer, last axis fastest (C order of F)
+                    if (++mu[j] <= G.degs[sm.s * sm.n + j]) break;
+                    mu[j] = 0;
+                }
+            }
+        }
+    }
+    const int64_t T = (int64_t)term_key.size();
+    plan.n_terms = T;
+
+    // ---- 5. coefficients C[T][d_out] in long double ---------------------------------------------------------
+    std::vector<ld> C((size_t)T * d_out, 0.0L);
+    if (offset)
+        for (int64_t o = 0; o < d_out; ++o) C[o] = (ld)offset[o];
+    {
+        const int64_t och_max = 256;
+        const int64_t n_och = (d_out + och_max - 1) / och_max;
+        auto work = [&](int64_t c_begin, int64_t c_end) {
+            std::vector<ld> Gt, tmp;
+            for (int64_t ch = c_begin; ch < c_end; ++ch) {
+                const int64_t o0 = ch * och_max, och = std::min(och_max, d_out - o0);
+                for (const Summand& sm : summands) {
+                    const GroupView& G = groups[sm.group];
+                    const int n = sm.n;
+                    const int64_t fsize = G.fsize();
+                    int m[kMaxLevels], pid[kMaxLevels];
+                    int64_t fstride[kMaxLevels], mstride[kMaxLevels];
+                    for (int j = n - 1; j >= 0; --j) {
+                        m[j] = (int)G.degs[sm.s * n + j] + 1;
+                        pid[j] = pair_id[{(int)G.dims[sm.s * n + j], m[j] - 1}];
+                        fstride[j] = (j == n - 1) ? 1 : fstride[j + 1] * (G.tau[j + 1] + 1);
+                        mstride[j] = (j == n - 1) ? 1 : mstride[j + 1] * m[j + 1];
+                    }
+                    const double* Fs = G.F + sm.s * d_out * fsize;
+                    Gt.resize((size_t)sm.count * och);
+                    int mu[kMaxLevels] = {0};
+                    for (int64_t idx = 0; idx < sm.count; ++idx) {
+                        int64_t foff = 0;
+                        for (int j = 0; j < n; ++j) foff += mu[j] * fstride[j];
+                        for (int64_t oo = 0; oo < och; ++oo) Gt[(size_t)(idx * och + oo)] = (ld)Fs[(o0 + oo) * fsize + foff];
+                        for (int j = n - 1; j >= 0; --j) {
+                            if (++mu[j] < m[j]) break;
+                            mu[j] = 0;
+                        }
+                    }
+                    for (int j = 0; j < n; ++j) {  // mode product with minv along axis j
+                        const int mj = m[j];
+                        const std::vector<ld>& Mi = pairs[pid[j]].minv;
+                        const int64_t inner = mstride[j], outer = sm.count / (inner * mj);
+                        tmp.resize((size_t)mj * och);
+                        for (int64_t u = 0; u < outer; ++u)
+                            for (int64_t v = 0; v < inner; ++v) {
+                                const int64_t base = u * mj * inner + v;
+                                for (int a = 0; a < mj; ++a)
+                                    std::memcpy(&tmp[(size_t)a * och], &Gt[(size_t)((base + a * inner) * och)], sizeof(ld) * och);
+                                for (int k = 0; k < mj; ++k) {
+                                    ld* dst = &Gt[(size_t)((base + k * inner) * och)];
+                                    for (int64_t oo = 0; oo < och; ++oo) {
+                                        ld acc = 0.0L;
+                                        for (int a = 0; a < mj; ++a) acc += Mi[(size_t)k * mj + a] * tmp[(size_t)a * och + oo];
+                                        dst[oo] = acc;
+                                    }
+                                }
+                            }
+                    }
+                    const ld z = (ld)sm.zeta;
+                    for (int64_t idx = 0; idx < sm.count; ++idx) {
+                        ld* dst = &C[(size_t)mu_terms[(size_t)(sm.mu_off + idx)] * d_out + o0];
+                        const ld* src = &Gt[(size_t)(idx * och)];
+                        for (int64_t oo = 0; oo < och; ++oo) dst[oo] += z * src[oo];
+                    }
+                }
+            }
+        };
+        unsigned hw = std::thread::hardware_concurrency();
+        int64_t nthr = std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, n_och));
+        if (nthr == 1) {
+            work(0, n_och);
+        } else {
+            std::vector<std::thread> pool;
+            for (int64_t t = 0; t < nthr; ++t)
+                pool.emplace_back(work, t * n_och / nthr, (t + 1) * n_och / nthr);
+            for (auto& th : pool) th.join();
+        }
+    }
+    plan.c0.resize((size_t)d_out);
+    for (int64_t o = 0; o < d_out; ++o) plan.c0[o] = (double)C[o];
+
+    // ---- 6. leading entries ----------------------------------------------------------------------------------
+    const int32_t E = eta_off[d_in];
+    plan.n_entries = E;
+    const int32_t Epad = (E + kBlockWidth - 1) / kBlockWidth * kBlockWidth;
+    plan.ent_dim.assign((size_t)Epad, 0);
+    plan.ent_deg.assign((size_t)Epad, 0);
+    plan.ent_eta.assign((size_t)Epad, 0);
+    for (int64_t d = 0; d < d_in; ++d)
+        for (int a = 1; a <= maxdeg[d]; ++a) {
+            const int32_t e = eta_off[d] + a - 1;
+            plan.ent_dim[e] = (int32_t)d;
+            plan.ent_deg[e] = a;
+            plan.ent_eta[e] = eta_off[d];
+        }
+
+    // ---- 7. rows (hot parts) with ancestors, sorted by level ------------------------------------------------
+    std::unordered_map<Key, int32_t, KeyHash> row_id;
+    std::vector<int32_t> rparent{-1}, rhslot{-1}, rlevel{0};
+    std::unordered_map<int64_t, int32_t> hot_id;
+    row_id[Key()] = 0;
+    // iterative "ensure row": walk prefixes of the (sorted) hot key from short to long
+    auto ensure_row = [&](const Key& h) -> int32_t {
+        int32_t parent = 0;
+        Key pre;
+        for (size_t i = 0; i < h.size(); ++i) {
+            pre.push_back(h[i]);
+            auto it = row_id.find(pre);
+            if (it != row_id.end()) {
+                parent = it->second;
+                continue;
+            }
+            auto hit = hot_id.find(h[i]);
+            int32_t hs;
+            if (hit == hot_id.end()) {
+                hs = (int32_t)plan.hot_dim.size();
+                hot_id.emplace(h[i], hs);
+                const int32_t dim = (int32_t)(h[i] / kCode), deg = (int32_t)(h[i] % kCode);
+                plan.hot_dim.push_back(dim);
+                plan.hot_deg.push_back(deg);
+                plan.hot_eta.push_back(eta_off[dim]);
+            } else {
+                hs = hit->second;
+            }
+            const int32_t id = (int32_t)rparent.size();
+            rparent.push_back(parent);
+            rhslot.push_back(hs);
+            rlevel.push_back((int32_t)i + 1);
+            row_id.emplace(pre, id);
+            parent = id;
+        }
+        return parent;
+    };
+    struct Nz {
+        int32_t block, row, lane, term;
+    };
+    std::vector<Nz> nz;
+    nz.reserve((size_t)T);
+    for (int32_t t = 1; t < T; ++t) {
+        const Key& key = term_key[t];
+        Key hot(key.begin(), key.end() - 1);
+        const int32_t r = ensure_row(hot);
+        const int64_t lead = key.back();
+        const int32_t e = eta_off[lead / kCode] + (int32_t)(lead % kCode) - 1;
+        nz.push_back({e / kBlockWidth, r, e % kBlockWidth, t});
+    }
+    const int32_t R = (int32_t)rparent.size();
+    plan.n_rows = R;
+    plan.n_hot = (int32_t)plan.hot_dim.size();
+    std::vector<int32_t> order(R), newid(R);
+    for (int32_t r = 0; r < R; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return rlevel[a] < rlevel[b]; });
+    for (int32_t i = 0; i < R; ++i) newid[order[i]] = i;
+    plan.row_parent.resize(R);
+    plan.row_hslot.resize(R);
+    int maxlevel = 0;
+    for (int32_t i = 0; i < R; ++i) {
+        const int32_t old = order[i];
+        plan.row_parent[i] = old == 0 ? 0 : newid[rparent[old]];
+        plan.row_hslot[i] = old == 0 ? 0 : rhslot[old];
+        maxlevel = std::max(maxlevel, rlevel[old]);
+    }
+    plan.n_levels = maxlevel + 1;
+    plan.level_off.assign((size_t)plan.n_levels + 1, 0);
+    for (int32_t i = 0; i < R; ++i) plan.level_off[rlevel[order[i]] + 1]++;
+    for (int l = 0; l < plan.n_levels; ++l) plan.level_off[l + 1] += plan.level_off[l];
+
+    // ---- 8. block-sparse coefficient matrix and work items ----------------------------------------------------
+    for (Nz& z : nz) z.row = newid[z.row];
+    std::sort(nz.begin(), nz.end(), [](const Nz& a, const Nz& b) {
+        if (a.block != b.block) return a.block < b.block;
+        if (a.row != b.row) return a.row < b.row;
+        return a.lane < b.lane;
+    });
+    struct Chunk {
+        int32_t block;
+        std::vector<int32_t> rows;
+        std::vector<double> coef;
+    };
+    std::vector<Chunk> chunks;
+    for (size_t i = 0; i < nz.size();) {
+        const int32_t b = nz[i].block;
+        // distinct rows of this block
+        size_t j = i;
+        std::vector<std::pair<int32_t, std::pair<size_t, size_t>>> rows;  // row -> [first, last)
+        while (j < nz.size() && nz[j].block == b) {
+            size_t k2 = j;
+            while (k2 < nz.size() && nz[k2].block == b && nz[k2].row == nz[j].row) ++k2;
+            rows.push_back({nz[j].row, {j, k2}});
+            j = k2;
+        }
+        // split evenly into chunks of at most kChunkRows rows
+        const size_t nr = rows.size(), nch = (nr + kChunkRows - 1) / kChunkRows;
+        for (size_t c = 0; c < nch; ++c) {
+            const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
+            Chunk ck;
+            ck.block = b;
+            ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
+            for (size_t r = r0; r < r1; ++r) {
+                ck.rows.push_back(rows[r].first);
+                for (size_t q = rows[r].second.first; q < rows[r].second.second; ++q)
+                    for (int64_t o = 0; o < d_out; ++o)
+                        ck.coef[((r - r0) * (size_t)d_out + o) * kBlockWidth + nz[q].lane] =
+                            (double)C[(size_t)nz[q].term * d_out + o];
+            }
+            chunks.push_back(std::move(ck));
+        }
+        i = j;
+    }
+    std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.rows.size() > b.rows.size(); });
+    plan.n_chunks = (int32_t)chunks.size();
+    plan.chunk_off.push_back(0);
+    for (const Chunk& ck : chunks) {
+        plan.chunk_block.push_back(ck.block);
+        plan.chunk_rows.insert(plan.chunk_rows.end(), ck.rows.begin(), ck.rows.end());
+        plan.coef.insert(plan.coef.end(), ck.coef.begin(), ck.coef.end());
+        plan.chunk_off.push_back((int32_t)plan.chunk_rows.size());
+    }
+    plan.padded_fma = (int64_t)plan.chunk_rows.size() * kBlockWidth;
+    return "";
+}
+
+void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y) {
+    const int64_t d_out = plan.d_out;
+    std::vector<double> pih((size_t)std::max(plan.n_hot, 1)), m((size_t)std::max(plan.n_rows, 1));
+    std::vector<double> acc((size_t)d_out);
+    for (int64_t p = 0; p < N; ++p) {
+        const double* xp = x + p * ldx;
+        for (int32_t h = 0; h < plan.n_hot; ++h) {
+            double v = 1.0;
+            for (int k = 0; k < plan.hot_deg[h]; ++k) v *= (xp[plan.hot_dim[h]] - plan.eta[plan.hot_eta[h] + k]);
+            pih[h] = v;
+        }
+        m[0] = 1.0;
+        for (int32_t r = 1; r < plan.n_rows; ++r) m[r] = m[plan.row_parent[r]] * pih[plan.row_hslot[r]];
+        double* yp = y + p * d_out;
+        for (int64_t o = 0; o < d_out; ++o) yp[o] = plan.c0[o];
+        for (int32_t c = 0; c < plan.n_chunks; ++c) {
+            const int32_t b = plan.chunk_block[c];
+            for (int lane = 0; lane < kBlockWidth; ++lane) {
+                const int32_t e = b * kBlockWidth + lane;
+                double v = 1.0;
+                for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
+                std::fill(acc.begin(), acc.end(), 0.0);
+                for (int32_t i = plan.chunk_off[c]; i < plan.chunk_off[c + 1]; ++i)
+                    for (int64_t o = 0; o < d_out; ++o)
+                        acc[o] = std::fma(plan.coef[((size_t)i * d_out + o) * kBlockWidth + lane], m[plan.chunk_rows[i]], acc[o]);
+                for (int64_t o = 0; o < d_out; ++o) yp[o] = std::fma(v, acc[o], yp[o]);
+            }
+        }
+    }
+}
+
+}  // namespace smx
+
+// ---- C entry points for the CPU-only test-suite (exported from libsmolyax_host.so) --------------------------------
+extern "C" {
+
+struct smxh_group {
+    int32_t n;
+    int64_t nn;
+    const int64_t* tau;
+    const double* F;
+    const double* nodes;
+    const double* weights;
+    const int64_t* dims;
+    const int64_t* degs;
+    const int64_t* zetas;
+    const double* quad;
+};
+
+static thread_local std::string g_plan_error;
+const char* smxh_plan_error() { return g_plan_error.c_str(); }
+
+void* smxh_plan_build(int64_t d_in, int64_t d_out, const double* offset, int32_t n_groups, const smxh_group* groups) {
+    std::vector<smx::GroupView> gv;
+    for (int32_t g = 0; g < n_groups; ++g) {
+        smx::GroupView v;
+        v.n = groups[g].n;
+        v.nn = groups[g].nn;
+        v.tau.assign(groups[g].tau, groups[g].tau + groups[g].n);
+        v.F = groups[g].F;
+        v.nodes = groups[g].nodes;
+        v.weights = groups[g].weights;
+        v.dims = groups[g].dims;
+        v.degs = groups[g].degs;
+        v.zetas = groups[g].zetas;
+        v.quad = groups[g].quad;
+        gv.push_back(v);
+    }
+    auto* plan = new smx::FastPlan();
+    g_plan_error = smx::build_fast_plan(d_in, d_out, offset, gv, *plan);
+    if (!g_plan_error.empty()) {
+        delete plan;
+        return nullptr;
+    }
+    return plan;
+}
+void smxh_plan_free(void* p) { delete static_cast<smx::FastPlan*>(p); }
+// stats: [n_terms, n_entries, n_rows, n_hot, n_chunks, padded_fma, n_levels, nested, n_summands, w_raw, w_pad]
+void smxh_plan_stats(void* p, int64_t* out) {
+    auto* pl = static_cast<smx::FastPlan*>(p);
+    int64_t v[11] = {pl->n_terms, pl->n_entries, pl->n_rows, pl->n_hot, pl->n_chunks, pl->padded_fma,
+                     pl->n_levels, pl->nested ? 1 : 0, pl->n_summands, pl->w_raw, pl->w_pad};
+    std::memcpy(out, v, sizeof(v));
+}
+// Verification aid, CPU tests only (see smx_plan.h).
+void smxh_plan_eval_host(void* p, const double* x, int64_t N, int64_t ldx, double* y) {
+    smx::eval_plan_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, y);
+}
+}

@@ -1,0 +1,88 @@
+// Host-side "plan": the device layout of the fast evaluation path, built from the reference's per-group layout.
+//
+// Mathematics.  The Smolyak interpolant  I(x) = sum_nu zeta_nu (x)_j I^{nu_j}[f](x)
+// (reference interpolation.py:283-302) is a polynomial in span{ prod_j x_j^{a_j} : a in Lambda }.  The plan
+// re-expresses it, exactly, in the product basis of monic Newton polynomials
+//        pi_{j,a}(x_j) = prod_{i<a} (x_j - eta_{j,i}),      Psi_alpha(x) = prod_{(j,a) in alpha} pi_{j,a}(x_j),
+//        I(x) = c_0 + sum_{alpha in Lambda, alpha != 0} c_alpha Psi_alpha(x),
+// where eta_j are the interpolation nodes of dimension j themselves (the nested sequence, or the Leja-ordered
+// nodes of the highest degree for non-nested rules).  The coefficients come from the value tensors F by the
+// 1-D change of basis "nodal values at the (deg+1) barycentric nodes -> Newton coefficients" along every axis,
+// times zeta, accumulated over summands in long double.  Each term is then split into its *leading entry*
+// (the pair with the largest dimension) and its *hot part* (the rest):
+//        I(x) = c_0 + sum_{e=(j,a)} pi_e(x_j) * sum_r  C[r][e] * m_r(x),       m_r = prod of the hot part r,
+// a block-sparse (rows r x entries e) contraction that the kernel in smx_fast.cu evaluates with the entries of a
+// block across lanes, the points in registers, and the row products m_r in shared memory.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace smx {
+
+struct GroupView {
+    int n = 0;
+    int64_t nn = 0;
+    std::vector<int64_t> tau;  // length n
+    const double* F = nullptr;
+    const double* nodes = nullptr;
+    const double* weights = nullptr;
+    const int64_t* dims = nullptr;
+    const int64_t* degs = nullptr;
+    const int64_t* zetas = nullptr;
+    const double* quad = nullptr;
+    int64_t fsize() const {
+        int64_t f = 1;
+        for (auto t : tau) f *= (t + 1);
+        return f;
+    }
+    int64_t tw() const {
+        int64_t m = 0;
+        for (auto t : tau) m = t > m ? t : m;
+        return m + 1;
+    }
+};
+
+constexpr int kBlockWidth = 16;    // entries per block: 4 lane-groups x 4 entries per lane
+constexpr int kChunkRows = 24;     // rows per work item
+constexpr int kMaxLevels = 16;
+
+struct FastPlan {
+    int64_t d_in = 0, d_out = 0;
+    bool nested = false;
+    int64_t n_summands = 0, w_raw = 0, w_pad = 0, n_terms = 0;
+
+    // leading entries, sorted by (dimension, degree); padded to a multiple of kBlockWidth
+    int32_t n_entries = 0;               // real entries
+    std::vector<int32_t> ent_dim;        // column of x
+    std::vector<int32_t> ent_deg;        // a >= 1  (0 for padding lanes: pi = 1, coefficients are zero)
+    std::vector<int32_t> ent_eta;        // offset of the dimension's centres in `eta`
+    std::vector<double> eta;             // centres, concatenated per dimension
+
+    // rows = distinct hot parts, sorted by level (number of pairs); row 0 is the empty product
+    int32_t n_rows = 0, n_levels = 0;
+    std::vector<int32_t> row_parent;     // m[r] = m[row_parent[r]] * pih[row_hslot[r]]
+    std::vector<int32_t> row_hslot;
+    std::vector<int32_t> level_off;      // rows of level l are [level_off[l], level_off[l+1])
+    int32_t n_hot = 0;                   // hot entries: (dim, deg) pairs that occur inside hot parts
+    std::vector<int32_t> hot_dim, hot_deg, hot_eta;
+
+    // work items: (entry block, slice of its row list); coefficients [row slot][d_out][kBlockWidth]
+    int32_t n_chunks = 0;
+    std::vector<int32_t> chunk_block;
+    std::vector<int32_t> chunk_off;      // size n_chunks+1, offsets into chunk_rows / coefficient row slots
+    std::vector<int32_t> chunk_rows;
+    std::vector<double> coef;
+    std::vector<double> c0;              // (d_out) constant term, includes the offset
+    int64_t padded_fma = 0;              // row slots * kBlockWidth
+};
+
+// Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).
+std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
+                            FastPlan& plan);
+
+// Verification aid for the CPU-only test-suite: evaluates the plan on the host in fp64 in the same order as
+// the kernel.  NOT a product path — nothing in smolyax_b200/ calls it; see tests/test_plan.py.
+void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y);
+
+}  // namespace smx

@@ -1,0 +1,313 @@
+r"""
+``SmolyakBarycentricInterpolator`` — drop-in for the evaluation path of the reference class of the same name
+(/root/reference/src/smolyax/interpolation.py:15-390): the Smolyak operator
+
+.. math::  I^{\Lambda}[f] = \sum_{\nu \in \Lambda_{k,t}} \zeta_{\Lambda,\nu}\, I^{\nu}[f]
+
+for vector-valued :math:`f : \mathbb R^{d_{in}} \to \mathbb R^{d_{out}}`, evaluated (``__call__``), differentiated
+(``gradient``) and integrated (``integral``) on a B200.
+
+What is the same as the reference: constructor keywords, ``set_f`` and its ``f_evals`` reuse dictionary, the
+counters ``n_f_evals`` / ``n_f_evals_new``, argument shapes, result shapes, assertion behaviour, the per-group
+tables (``reference_layout()`` returns exactly the six arrays of interpolation.py:230-235, bit for bit).
+What is different: the tables go through ``smx_create`` into the device layout of DESIGN.md and every call is a
+handful of CUDA kernel launches instead of a Python loop of XLA dispatches.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import itertools as it
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, indices, nodes  # noqa: F401
+
+_CODE = 1 << 20  # (dim, deg) -> dim * _CODE + deg
+
+
+def _host_weights(pts: np.ndarray) -> np.ndarray:
+    """Barycentric weights on the host, same expression as reference barycentric.py:28-31 (setup only)."""
+    diffs = pts[:, None] - pts
+    diffs = np.where(diffs == 0, 1, diffs)
+    return np.prod(1 / diffs, axis=0)
+
+
+class SmolyakBarycentricInterpolator:
+    """Smolyak interpolation operator with barycentric tensor-product interpolants, evaluated on the GPU."""
+
+    # ------------------------------------------------------------------ properties (interpolation.py:31-49)
+    @property
+    def d_in(self) -> int:
+        """Input dimension of target function and interpolant"""
+        return self._d_in
+
+    @property
+    def d_out(self) -> int:
+        """Output dimension of target function and interpolant"""
+        return self._d_out
+
+    @property
+    def n_f_evals(self) -> int:
+        """Number of function evaluations (== number of interpolation nodes) used by the interpolator"""
+        return self._n_f_evals
+
+    @property
+    def n_f_evals_new(self) -> int:
+        """Number of function evaluations that were not reused from previous computations"""
+        return self._n_f_evals_new
+
+    # ------------------------------------------------------------------ construction (interpolation.py:51-113)
+    def __init__(self, node_gen=None, k: Sequence[float] = None, d_out: int = None, t: float = None,
+                 f: Callable = None, *, n_inputs: int = None, memory_limit: float = 4.0, method: str = "auto",
+                 device: int = None, batched_f: bool = False) -> None:
+        r"""
+        Parameters (all accepted as keywords, as in the reference)
+        ----------
+        node_gen : nodes.Generator
+            One 1-D node family per input dimension.
+        k : sequence of float
+            Increasing anisotropy weights of the multi-index set; ``d_in = len(k)``.
+        d_out : int
+            Output dimension of the target function.
+        t : float
+            Threshold of the multi-index set.
+        f : callable, optional
+            Target function, called with one point ``(d_in,)``; see :meth:`set_f`.
+        n_inputs : int, optional
+            Expected batch size; used to size the staging buffers of the host pipeline ahead of the first call.
+        memory_limit : float
+            Accepted for compatibility.  The fused kernels have no per-summand intermediates, so nothing is batched.
+        method : {"auto", "barycentric"}
+            "auto": values through the hierarchical fast path, gradient/integral through the per-summand kernels.
+            "barycentric": every entry point through the per-summand second-barycentric-form kernels.
+        device : int, optional
+            CUDA ordinal (default: the current torch device).
+        batched_f : bool
+            If true ``set_f`` calls ``f`` once with all new nodes ``(n_new, d_in)`` instead of once per node.
+        """
+        assert node_gen is not None and k is not None and d_out is not None and t is not None
+        assert method in ("auto", "barycentric")
+        self._d_in = len(k)
+        self._d_out = int(d_out)
+        self._node_gen = node_gen
+        self._is_nested = node_gen.is_nested
+        self._k = k
+        self._t = t
+        self._method = method
+        self._device = (torch.cuda.current_device() if torch.cuda.is_available() else 0) if device is None else int(device)
+        self._batched_f = batched_f
+        self._memory_limit = memory_limit
+        self._n_inputs = n_inputs
+
+        self._layout = None
+        self._handle = None
+        self._n_f_evals = indices.nodeset_cardinality(k, t, nested=self._is_nested)
+        self._n_f_evals_new = 0
+        if f is not None:
+            self.set_f(f=f)
+
+    def __del__(self):
+        self._release()
+
+    def _release(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle is not None and _lib is not None:
+            _lib.lib.smx_destroy(handle)
+
+    # ------------------------------------------------------------------ set_f (interpolation.py:115-239)
+    def set_f(self, *, f: Callable, f_evals: dict = None) -> dict:
+        """Evaluate (or reuse from ``f_evals``) the target function at the interpolation nodes and build the device
+        tables.  Returns the updated dictionary of evaluations: flat ``{mu_tuple: value}`` for nested rules,
+        ``{nu: {mu_tuple: value}}`` otherwise (reference interpolation.py:119,155-163,208-228)."""
+        layout, f_evals = self._assemble(f, {} if f_evals is None else f_evals)
+        self._layout = layout
+        self._release()
+        flags = _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
+        with torch.cuda.device(self._device):
+            self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
+        return f_evals
+
+    def _assemble(self, f: Callable, f_evals: dict):
+        """Host half of ``set_f``: the reference's per-group tables as NumPy arrays (no GPU needed)."""
+        gen = self._node_gen
+        zero = np.array([g(0)[0] for g in gen])
+        offsets, dims_all, degs_all, zetas_all = indices.nonzero_arrays(self._k, self._t)
+        lengths = np.diff(offsets)
+        layout = {"offset": np.zeros(self._d_out)}
+
+        for n in sorted(set(lengths.tolist()), key=lambda v: np.flatnonzero(lengths == v)[0]):
+            sel = np.flatnonzero(lengths == n)  # summands of this group, in the order of the reference's walk
+            zetas = zetas_all[sel].astype(np.int64)
+            if n == 0:
+                assert len(sel) == 1
+                store = f_evals if self._is_nested else f_evals.get((), {})
+                if () not in store:
+                    store[()] = f(zero.copy())
+                    self._n_f_evals_new += 1
+                if not self._is_nested:
+                    f_evals[()] = store
+                layout["offset"] = np.asarray(int(zetas[0]) * np.asarray(store[()], dtype=float), dtype=float) * np.ones(self._d_out)
+                continue
+
+            nn = len(sel)
+            gather = offsets[sel][:, None] + np.arange(n)[None, :]
+            dims_in, degs_in = dims_all[gather].astype(np.int64), degs_all[gather].astype(np.int64)
+            # active dimensions by degree, descending; ties keep ascending dimension (interpolation.py:175)
+            order = np.argsort(-degs_in, axis=1, kind="stable")
+            sorted_dims = np.take_along_axis(dims_in, order, axis=1)
+            sorted_degs = np.take_along_axis(degs_in, order, axis=1)
+
+            tau = tuple(int(v) for v in sorted_degs.max(axis=0))
+            tw = max(tau) + 1
+            node_tab = np.zeros((nn, n, tw))
+            weight_tab = np.zeros((nn, n, tw))
+            quad_tab = np.zeros((nn, n, tw))
+            cache = {}
+            for slot in range(n):
+                codes = sorted_dims[:, slot] * _CODE + sorted_degs[:, slot]
+                for code in np.unique(codes):
+                    dim, deg = int(code // _CODE), int(code % _CODE)
+                    key = (id(gen[dim]), deg)
+                    if key not in cache:
+                        pts = np.asarray(gen[dim](deg), dtype=float)
+                        cache[key] = (pts, _host_weights(pts), np.asarray(gen[dim].get_quadrature_weights(deg), dtype=float))
+                    pts, wts, qts = cache[key]
+                    rows = np.flatnonzero(codes == code)
+                    node_tab[rows, slot, : deg + 1] = pts
+                    weight_tab[rows, slot, : deg + 1] = wts
+                    quad_tab[rows, slot, : len(qts)] = qts
+
+            F = np.zeros((nn,) + tuple(v + 1 for v in tau) + (self._d_out,))
+            pending = []  # (summand, mu, key, point) for batched evaluation
+            for i in range(nn):
+                nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
+                store = f_evals if self._is_nested else f_evals.get(nu, {})
+                s_i = sorted_dims[i]
+                by_dim = np.argsort(s_i)
+                x = zero.copy()
+                F_i = F[i]
+                for mu in it.product(*[range(int(v) + 1) for v in sorted_degs[i]]):
+                    key = tuple((int(s_i[j]), mu[j]) for j in by_dim if mu[j] > 0)
+                    if key not in store:
+                        x[s_i] = [node_tab[i, j, mu[j]] for j in range(n)]
+                        if self._batched_f:
+                            store[key] = None
+                            pending.append((store, key, x.copy()))
+                        else:
+                            store[key] = f(x)
+                        self._n_f_evals_new += 1
+                    if not self._batched_f:
+                        F_i[mu] = store[key]
+                if not self._is_nested:
+                    f_evals[nu] = store
+            if self._batched_f:
+                if pending:
+                    vals = np.asarray(f(np.stack([p[2] for p in pending])), dtype=float).reshape(len(pending), -1)
+                    for (store, key, _), v in zip(pending, vals):
+                        store[key] = v if self._d_out > 1 else (v[0] if v.size == 1 else v)
+                for i in range(nn):
+                    nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
+                    store = f_evals if self._is_nested else f_evals[nu]
+                    s_i = sorted_dims[i]
+                    by_dim = np.argsort(s_i)
+                    for mu in it.product(*[range(int(v) + 1) for v in sorted_degs[i]]):
+                        F[i][mu] = store[tuple((int(s_i[j]), mu[j]) for j in by_dim if mu[j] > 0)]
+
+            layout[f"F_{n}"] = np.ascontiguousarray(np.moveaxis(F, -1, 1))
+            layout[f"nodes_{n}"] = node_tab
+            layout[f"weights_{n}"] = weight_tab
+            layout[f"dims_{n}"] = sorted_dims
+            layout[f"degs_{n}"] = sorted_degs
+            layout[f"zetas_{n}"] = zetas
+            layout[f"quad_{n}"] = quad_tab
+
+        return layout, f_evals
+
+    # ------------------------------------------------------------------ helpers
+    def reference_layout(self) -> dict:
+        """The per-group tables exactly as the reference keeps them after ``set_f`` (interpolation.py:230-235), as
+        NumPy arrays keyed ``offset``, ``F_n``, ``nodes_n``, ``weights_n``, ``dims_n``, ``degs_n``, ``zetas_n``
+        (+ ``quad_n``, the tables of interpolation.py:361-379)."""
+        assert self._layout is not None, "The operator has not yet been set up for a target function via `set_f`."
+        return self._layout
+
+    def device_info(self) -> dict:
+        """Sizes of the device layout (smx_get_info)."""
+        assert self._handle is not None, "The operator has not yet been set up for a target function via `set_f`."
+        return _lib.info(self._handle)
+
+    def _validate_input(self, x):
+        """interpolation.py:253-262: set-up check, ``(d_in,)`` -> ``(1, d_in)``, column-count assertion."""
+        assert self._handle is not None, "The operator has not yet been set up for a target function via `set_f`."
+        if isinstance(x, torch.Tensor):
+            if x.dim() == 1 and x.shape[0] == self._d_in:
+                x = x[None, :]
+            assert x.dim() == 2 and x.shape[1] == self._d_in, f"{tuple(x.shape)[-1]} != {self._d_in}"
+            x = x.to(torch.float64)
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            kind = "cuda" if x.is_cuda else "torch_cpu"
+        else:
+            x = np.asarray(x, dtype=np.float64)
+            if x.shape == (self._d_in,):
+                x = x[None, :]
+            assert x.ndim == 2 and x.shape[1] == self._d_in, f"{x.shape[-1]} != {self._d_in}"
+            x = np.ascontiguousarray(x)
+            kind = "numpy"
+        self._n_inputs = x.shape[0]
+        return x, kind
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ __call__ (interpolation.py:264-304)
+    def __call__(self, x):
+        """Evaluate the interpolant at ``x`` of shape ``(n_points, d_in)`` or ``(d_in,)``; result ``(n_points, d_out)``.
+
+        A CUDA ``torch`` tensor is evaluated in place on the current stream and a CUDA tensor is returned without
+        synchronising (like the reference's un-synchronised ``jax.Array``).  Host input (NumPy, or a CPU tensor —
+        pinned for full speed) goes through the pipelined host path and returns a host array of the same kind.
+        """
+        x, kind = self._validate_input(x)
+        n_points = x.shape[0]
+        lib = _lib.lib
+        with torch.cuda.device(self._device):
+            if kind == "cuda":
+                y = torch.empty((n_points, self._d_out), dtype=torch.float64, device=x.device)
+                _lib.check(lib.smx_eval(self._handle, x.data_ptr(), n_points, x.stride(0), y.data_ptr(), self._stream()), "smx_eval")
+                return y
+            if kind == "torch_cpu":
+                y = torch.empty((n_points, self._d_out), dtype=torch.float64, pin_memory=x.is_pinned())
+                _lib.check(lib.smx_eval_host(self._handle, x.data_ptr(), n_points, x.stride(0), y.data_ptr(), 0), "smx_eval_host")
+                return y
+            y = np.empty((n_points, self._d_out))
+            _lib.check(lib.smx_eval_host(self._handle, x.ctypes.data, n_points, x.shape[1], y.ctypes.data, 0), "smx_eval_host")
+            return y
+
+    # ------------------------------------------------------------------ gradient (interpolation.py:306-345)
+    def gradient(self, x):
+        """Gradient of the interpolant at ``x``: ``(n_points, d_out, d_in)``.  As in the reference, a coordinate that
+        sits exactly on an interpolation node of its dimension yields ``NaN`` in that dimension."""
+        x, kind = self._validate_input(x)
+        n_points = x.shape[0]
+        with torch.cuda.device(self._device):
+            xd = x if kind == "cuda" else (x.cuda() if kind == "torch_cpu" else torch.from_numpy(x).cuda())
+            J = torch.empty((n_points, self._d_out, self._d_in), dtype=torch.float64, device=xd.device)
+            _lib.check(_lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, xd.stride(0), J.data_ptr(), self._stream()),
+                       "smx_gradient")
+            if kind == "cuda":
+                return J
+            return J.cpu() if kind == "torch_cpu" else J.cpu().numpy()
+
+    # ------------------------------------------------------------------ integral (interpolation.py:347-390)
+    def integral(self):
+        """Integral of the interpolant w.r.t. the probability measure of the node family (= Smolyak quadrature of
+        ``f``): shape ``(d_out,)``, synchronised like the reference's ``block_until_ready``."""
+        assert self._handle is not None, "The operator has not yet been set up for a target function via `set_f`."
+        with torch.cuda.device(self._device):
+            q = torch.empty(self._d_out, dtype=torch.float64, device="cuda")
+            _lib.check(_lib.lib.smx_integral(self._handle, q.data_ptr(), self._stream()), "smx_integral")
+            return q.cpu().numpy()
