@@ -122,12 +122,17 @@ class SmolyakBarycentricInterpolator:
         tables.  Returns the updated dictionary of evaluations: flat ``{mu_tuple: value}`` for nested rules,
         ``{nu: {mu_tuple: value}}`` otherwise (reference interpolation.py:119,155-163,208-228)."""
         layout, f_evals = self._assemble(f, {} if f_evals is None else f_evals)
+        self.set_layout(layout)
+        return f_evals
+
+    def set_layout(self, layout: dict) -> None:
+        """Build the device tables from an already assembled reference layout (``reference_layout()`` of another
+        instance, e.g. received through ``dist.broadcast_layout``) instead of evaluating ``f`` again."""
         self._layout = layout
         self._release()
         flags = _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
         with torch.cuda.device(self._device):
             self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
-        return f_evals
 
     def _assemble(self, f: Callable, f_evals: dict):
         """Host half of ``set_f``: the reference's per-group tables as NumPy arrays (no GPU needed)."""

@@ -1,0 +1,157 @@
+"""GPU parity (run with -m gpu on a B200): the CUDA paths, called through the C-ABI, against (a) the outputs of the
+unmodified reference stored in tests/golden and (b) the CPU oracle on the same inputs.
+
+Tolerances (fp64):
+  * per-summand (second barycentric form) kernels vs oracle: same formulas, different summation order ->
+    1e-13 of the summand magnitude  sum_nu |zeta_nu I_nu f|.
+  * fast path vs reference: 1e-12 of the summand magnitude — the bound north_star states, measured in the only
+    norm in which two correct fp64 implementations can meet it (the reference's own rounding noise
+    is 1e-13..4e-11 pointwise), plus "at least as close to the 80-bit referee as the reference is".
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (ALL_CASES, BIG_CASES, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double,
+                     scaled_error)
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(case, **extra):
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    g = load(case)
+    kwargs, f = interpolator_inputs(g)
+    return g, SmolyakBarycentricInterpolator(**kwargs, f=f, **extra)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_values_fast_path(case):
+    from oracle import oracle
+
+    g, ip = _build(case)
+    assert ip.device_info()["has_fast_path"] == 1
+    x = g["x"]
+    y = ip(x)
+    assert isinstance(y, np.ndarray) and y.shape == g["y_ref"].shape
+    assert scaled_error(y, g["y_ref"], g["cond_abs"]) < 1e-12
+    y_orc = oracle.evaluate(ip.reference_layout(), x)
+    assert scaled_error(y, y_orc, g["cond_abs"]) < 1e-12
+    y_ld = long_double(g, "y")
+    scale = np.max(np.abs(g["y_ref"]))
+    err_new = np.max(np.abs((y - y_ld).astype(float))) / scale
+    err_ref = np.max(np.abs((g["y_ref"] - y_ld).astype(float))) / scale
+    assert err_new <= max(err_ref, 5e-14)
+    # device-resident input gives the same bits as the host pipeline; single point keeps the (1, d_out) shape
+    y_dev = ip(torch.from_numpy(x).cuda())
+    assert y_dev.is_cuda and np.array_equal(y_dev.cpu().numpy(), y)
+    assert ip(x[0]).shape == (1, ip.d_out) and np.array_equal(ip(x[0])[0], y[0])
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_values_barycentric_kernels(case):
+    from oracle import oracle
+
+    g, ip = _build(case, method="barycentric")
+    assert ip.device_info()["has_fast_path"] == 0
+    y = ip(g["x"])
+    y_orc = oracle.evaluate(ip.reference_layout(), g["x"])
+    assert scaled_error(y, y_orc, g["cond_abs"]) < 1e-13
+    assert scaled_error(y, g["y_ref"], g["cond_abs"]) < 1e-13
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_gradient(case):
+    from oracle import oracle
+
+    g, ip = _build(case)
+    J_ref = g["J_ref"]
+    x = g["x"][: len(J_ref)]
+    J = ip.gradient(x)
+    assert J.shape == J_ref.shape == (len(x), ip.d_out, ip.d_in)
+    assert np.array_equal(np.isnan(J), np.isnan(J_ref))  # NaN where a coordinate sits on a node, as the reference
+    ok = ~np.isnan(J_ref)
+    scale = max(1.0, float(np.max(np.abs(J_ref[ok])))) if ok.any() else 1.0
+    assert np.max(np.abs(J[ok] - J_ref[ok]), initial=0.0) <= 1e-9 * scale
+    J_orc = oracle.gradient(ip.reference_layout(), x)
+    assert np.max(np.abs(J[ok] - J_orc[ok]), initial=0.0) <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_integral(case):
+    g, ip = _build(case)
+    Q = ip.integral()
+    assert Q.shape == (ip.d_out,)
+    Q_ld = long_double(g, "Q")
+    err_new = np.max(np.abs((Q - Q_ld).astype(float)))
+    err_ref = np.max(np.abs((g["Q_ref"] - Q_ld).astype(float)))
+    assert err_new <= max(10 * err_ref, 1e-11 * max(1.0, float(np.max(np.abs(g["Q_ref"])))))
+
+
+@pytest.mark.parametrize("case", LAYOUT_CASES)
+def test_seam_twins_on_reference_layout(case):
+    """smx_group_eval / smx_group_gradient / smx_group_integral with DEVICE pointers to the reference's own arrays."""
+    from oracle import oracle
+    from smolyax_b200 import _lib
+
+    g = load(case)
+    layout = golden_layout(g)
+    d_out, x = int(g["d_out"]), g["x"]
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in layout.items()}
+    xd = torch.from_numpy(x).cuda()
+    y = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(layout["offset"], (len(x), d_out)))).cuda()
+    J = torch.zeros((len(x), d_out, x.shape[1]), dtype=torch.float64, device="cuda")
+    q = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(layout["offset"], (d_out,)))).cuda()
+    arr, n_groups, keep = _lib.pack_groups(dev, lambda a, dt: (a, a.data_ptr()))
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for i in range(n_groups):
+        one = ctypes.byref(arr[i]) if False else ctypes.pointer(arr[i])
+        _lib.check(_lib.lib.smx_group_eval(xd.data_ptr(), len(x), x.shape[1], x.shape[1], one, d_out, y.data_ptr(), 1, stream))
+        _lib.check(_lib.lib.smx_group_gradient(xd.data_ptr(), len(x), x.shape[1], x.shape[1], one, d_out, J.data_ptr(), 1, stream))
+        _lib.check(_lib.lib.smx_group_integral(one, d_out, q.data_ptr(), 1, stream))
+    torch.cuda.synchronize()
+    assert scaled_error(y.cpu().numpy(), oracle.evaluate(layout, x), g["cond_abs"]) < 1e-13
+    J_orc = oracle.gradient(layout, x)
+    Jh = J.cpu().numpy()
+    assert np.array_equal(np.isnan(Jh), np.isnan(J_orc))
+    ok = ~np.isnan(J_orc)
+    assert np.max(np.abs(Jh[ok] - J_orc[ok]), initial=0.0) <= 1e-10 * max(1.0, float(np.max(np.abs(J_orc[ok]), initial=0.0)))
+    assert np.allclose(q.cpu().numpy(), oracle.integral(layout), rtol=1e-11, atol=1e-12)
+
+
+def test_barycentric_module_functions():
+    """The reference's barycentric.py API, one summand at a time (barycentric.py:13,34,69,126,158)."""
+    from oracle import oracle
+    from smolyax_b200 import barycentric
+
+    g = load("medium_00")
+    layout = golden_layout(g)
+    x = g["x"]
+    n = 2
+    F, nd, wt = layout[f"F_{n}"], layout[f"nodes_{n}"], layout[f"weights_{n}"]
+    dims, degs, zetas = layout[f"dims_{n}"], layout[f"degs_{n}"], layout[f"zetas_{n}"]
+    for s in range(min(5, len(zetas))):
+        one = {"offset": np.zeros(F.shape[1]), f"F_{n}": F[s:s + 1], f"nodes_{n}": nd[s:s + 1], f"weights_{n}": wt[s:s + 1],
+               f"dims_{n}": dims[s:s + 1], f"degs_{n}": degs[s:s + 1], f"zetas_{n}": zetas[s:s + 1]}
+        val = barycentric.evaluate_tensor_product_interpolant(x, F[s], nd[s], wt[s], dims[s], degs[s], int(zetas[s]))
+        assert np.allclose(val, oracle.evaluate(one, x), rtol=1e-13, atol=1e-14)
+        grad = barycentric.evaluate_tensor_product_gradient(x, F[s], nd[s], wt[s], dims[s], degs[s], int(zetas[s]))
+        ref = oracle.gradient(one, x)
+        assert np.array_equal(np.isnan(grad), np.isnan(ref))
+        assert np.allclose(grad[~np.isnan(ref)], ref[~np.isnan(ref)], rtol=1e-11, atol=1e-12)
+    pts = nd[0, 0, : degs[0, 0] + 1]
+    w = barycentric.compute_weights(pts)
+    assert np.allclose(w, oracle.compute_weights(pts), rtol=1e-15) and np.allclose(w, wt[0, 0, : len(pts)], rtol=1e-14)
+    xs = x[:, dims[0, 0]]
+    xs = np.concatenate([xs[~np.isin(xs, pts)], pts[:1]])  # regular points, then one that sits on node 0
+    b = barycentric.evaluate_basis_unnormalized(xs[:, None], nd[0, 0], wt[0, 0], int(degs[0, 0]))
+    db = barycentric.evaluate_basis_gradient_unnormalized(xs[:, None], nd[0, 0], wt[0, 0], int(degs[0, 0]))
+    m = nd.shape[2]
+    assert b.shape == db.shape == (len(xs), m)
+    k = int(degs[0, 0]) + 1
+    assert np.allclose(b[:-1, :k], wt[0, 0, :k] / (xs[:-1, None] - nd[0, 0, :k])) and np.all(b[:, k:] == 0)
+    assert np.array_equal(b[-1, :k], np.eye(k)[0]) and np.isnan(db[-1, 0]) and np.all(db[:, k:] == 0)
+    assert np.allclose(db[:-1, :k], -wt[0, 0, :k] / (xs[:-1, None] - nd[0, 0, :k]) ** 2)
