@@ -92,7 +92,7 @@ def _one_summand(x, F, xi_list, w_list, sorted_dims, sorted_degs, zeta, gradient
     else:
         out = torch.empty((n_points, d_out), dtype=torch.float64, device=d_x.device)
         fn = _lib.lib.smx_group_eval
-    _lib.check(fn(d_x.data_ptr(), n_points, d_x.stride(0), d_in, arr, d_out, out.data_ptr(), 0, _stream()),
+    _lib.check(fn(d_x.data_ptr(), n_points, d_x.stride(0) if n_points > 1 else d_in, d_in, arr, d_out, out.data_ptr(), 0, _stream()),
                "evaluate_tensor_product")
     del keep
     return _back(out, on_dev)

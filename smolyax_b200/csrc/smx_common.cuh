@@ -69,25 +69,19 @@ int device_basis(const double* x, int64_t N, const double* xi, const double* w, 
 // fast path (smx_fast.cu)
 struct FastDevice {
     int64_t d_in = 0, d_out = 0;
-    int32_t n_entries_padded = 0, n_rows = 0, n_levels = 0, n_hot = 0, n_chunks = 0;
+    int32_t n_tab = 1, n_hot = 0, n_levels = 1, n_chunks = 0, hot_dims = 0, n_pairs = 0;
     int32_t level_off[kMaxLevels + 2] = {0};
     int32_t* ent_dim = nullptr;
-    int32_t* ent_deg = nullptr;
-    int32_t* ent_eta = nullptr;
     double* eta = nullptr;
-    int32_t* row_parent = nullptr;
-    int32_t* row_hslot = nullptr;
-    int32_t* hot_dim = nullptr;
-    int32_t* hot_deg = nullptr;
-    int32_t* hot_eta = nullptr;
-    int32_t* chunk_block = nullptr;
-    int32_t* chunk_off = nullptr;
-    int32_t* chunk_rows = nullptr;
+    int32_t* tab_pairs = nullptr;
+    int32_t* hot_off = nullptr;
+    int32_t* chunk_dir = nullptr;
+    int32_t* chunk_meta = nullptr;
     double* coef = nullptr;
     double* c0 = nullptr;
-    int max_ent_deg = 0;
     int64_t bytes = 0;
     int sm_count = 148;
+    int warps = 4;  // warps per CTA of the evaluation kernel (4: two CTAs per SM, 8: one)
 };
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);

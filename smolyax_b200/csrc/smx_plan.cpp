@@ -300,108 +300,126 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     plan.c0.resize((size_t)d_out);
     for (int64_t o = 0; o < d_out; ++o) plan.c0[o] = (double)C[o];
 
-    // ---- 6. leading entries ----------------------------------------------------------------------------------
-    const int32_t E = eta_off[d_in];
-    plan.n_entries = E;
-    const int32_t Epad = (E + kBlockWidth - 1) / kBlockWidth * kBlockWidth;
-    plan.ent_dim.assign((size_t)Epad, 0);
-    plan.ent_deg.assign((size_t)Epad, 0);
-    plan.ent_eta.assign((size_t)Epad, 0);
-    for (int64_t d = 0; d < d_in; ++d)
-        for (int a = 1; a <= maxdeg[d]; ++a) {
-            const int32_t e = eta_off[d] + a - 1;
-            plan.ent_dim[e] = (int32_t)d;
-            plan.ent_deg[e] = a;
-            plan.ent_eta[e] = eta_off[d];
-        }
-
-    // ---- 7. rows (hot parts) with ancestors, sorted by level ------------------------------------------------
-    std::unordered_map<Key, int32_t, KeyHash> row_id;
-    std::vector<int32_t> rparent{-1}, rhslot{-1}, rlevel{0};
-    std::unordered_map<int64_t, int32_t> hot_id;
+    // ---- 6. hot parts: every term minus its leading (largest-dimension) pair ---------------------------------
+    std::unordered_map<Key, int32_t, KeyHash> row_id;  // hot part -> provisional row id (0 = empty product)
+    std::vector<Key> row_key{Key()};
     row_id[Key()] = 0;
-    // iterative "ensure row": walk prefixes of the (sorted) hot key from short to long
-    auto ensure_row = [&](const Key& h) -> int32_t {
-        int32_t parent = 0;
+    int hot_dim_max = -1;
+    std::vector<int32_t> term_row((size_t)T, 0);
+    for (int32_t t = 1; t < T; ++t) {
+        const Key& key = term_key[t];
         Key pre;
-        for (size_t i = 0; i < h.size(); ++i) {
-            pre.push_back(h[i]);
+        int32_t id = 0;
+        for (size_t i = 0; i + 1 < key.size(); ++i) {  // all prefixes are rows too (parents)
+            pre.push_back(key[i]);
+            hot_dim_max = std::max(hot_dim_max, (int)(key[i] / kCode));
             auto it = row_id.find(pre);
-            if (it != row_id.end()) {
-                parent = it->second;
-                continue;
-            }
-            auto hit = hot_id.find(h[i]);
-            int32_t hs;
-            if (hit == hot_id.end()) {
-                hs = (int32_t)plan.hot_dim.size();
-                hot_id.emplace(h[i], hs);
-                const int32_t dim = (int32_t)(h[i] / kCode), deg = (int32_t)(h[i] % kCode);
-                plan.hot_dim.push_back(dim);
-                plan.hot_deg.push_back(deg);
-                plan.hot_eta.push_back(eta_off[dim]);
+            if (it == row_id.end()) {
+                id = (int32_t)row_key.size();
+                row_id.emplace(pre, id);
+                row_key.push_back(pre);
             } else {
-                hs = hit->second;
+                id = it->second;
             }
-            const int32_t id = (int32_t)rparent.size();
-            rparent.push_back(parent);
-            rhslot.push_back(hs);
-            rlevel.push_back((int32_t)i + 1);
-            row_id.emplace(pre, id);
-            parent = id;
         }
-        return parent;
+        term_row[t] = id;
+    }
+    plan.n_rows = (int32_t)row_key.size();
+    plan.hot_dims = hot_dim_max + 1;
+
+    // ---- 7. leading entries: hot prefix, block padding, even-aligned cold blocks --------------------------------
+    std::vector<int32_t> ent_index((size_t)d_in, -1);  // entry of (dim, 1); (dim, a) is ent_index[dim] + a - 1
+    auto push_entry = [&](int32_t dim, int32_t deg, int32_t tab) {
+        plan.ent_dim.push_back(dim);
+        plan.ent_deg.push_back(deg);
+        plan.ent_eta.push_back(eta_off[dim]);
+        plan.ent_tab.push_back(tab);
+        plan.ent_eta0.push_back(maxdeg[dim] > 0 ? plan.eta[eta_off[dim]] : 0.0);
     };
+    auto pad_block = [&]() {
+        while (plan.ent_dim.size() % kBlockWidth) push_entry(0, 0, 0);
+    };
+    for (int64_t d = 0; d < d_in; ++d) {
+        if (maxdeg[d] == 0) continue;
+        const bool hot = d <= hot_dim_max;
+        // a cold block that would start on an odd column gets the column before it as a dummy first entry
+        if (!hot && plan.ent_dim.size() % kBlockWidth == 0 && (d & 1)) push_entry((int32_t)d - 1, 0, 0);
+        ent_index[d] = (int32_t)plan.ent_dim.size();
+        for (int a = 1; a <= maxdeg[d]; ++a) {
+            push_entry((int32_t)d, a, hot ? plan.n_hot + 1 : 0);
+            if (hot) ++plan.n_hot;
+            ++plan.n_entries;
+        }
+        if (hot && (d == hot_dim_max)) pad_block();  // cold entries start on a block boundary
+    }
+    pad_block();
+    // hot entry h (in entry order) sits in table row 1 + h; map (dim, deg) code -> table row
+    std::unordered_map<int64_t, int32_t> hot_tab;
+    for (size_t e = 0; e < plan.ent_dim.size(); ++e)
+        if (plan.ent_tab[e] > 0) hot_tab[(int64_t)plan.ent_dim[e] * kCode + plan.ent_deg[e]] = plan.ent_tab[e];
+
+    // ---- 8. value table: level-1 rows alias the hot entries, level >= 2 rows are appended level by level ---------
+    const int32_t R = plan.n_rows;
+    std::vector<int32_t> row_tab((size_t)R, 0);
+    int maxlevel = 0;
+    for (int32_t r = 0; r < R; ++r) maxlevel = std::max(maxlevel, (int)row_key[r].size());
+    plan.n_levels = maxlevel + 1;
+    plan.level_off.assign((size_t)plan.n_levels + 2, 0);
+    int32_t next = 1 + plan.n_hot;
+    for (int32_t r = 0; r < R; ++r)
+        if (row_key[r].size() == 1) row_tab[r] = hot_tab.at(row_key[r][0]);
+    for (int l = 2; l <= maxlevel; ++l) {
+        plan.level_off[l] = next;
+        for (int32_t r = 0; r < R; ++r) {  // provisional ids are in creation order: parents precede children
+            if ((int)row_key[r].size() != l) continue;
+            Key parent(row_key[r].begin(), row_key[r].end() - 1);
+            row_tab[r] = next++;
+            plan.tab_parent.push_back(row_tab[row_id.at(parent)]);
+            plan.tab_hot.push_back(hot_tab.at(row_key[r].back()));
+        }
+        plan.level_off[l + 1] = next;
+    }
+    for (int l = maxlevel + 1; l < (int)plan.level_off.size(); ++l) plan.level_off[l] = next;
+    if (maxlevel < 2) plan.level_off.assign(plan.level_off.size(), next);
+    plan.n_tab = next;
+
+    // ---- 9. block-sparse coefficient matrix and work items ------------------------------------------------------
     struct Nz {
         int32_t block, row, lane, term;
     };
     std::vector<Nz> nz;
     nz.reserve((size_t)T);
     for (int32_t t = 1; t < T; ++t) {
-        const Key& key = term_key[t];
-        Key hot(key.begin(), key.end() - 1);
-        const int32_t r = ensure_row(hot);
-        const int64_t lead = key.back();
-        const int32_t e = eta_off[lead / kCode] + (int32_t)(lead % kCode) - 1;
-        nz.push_back({e / kBlockWidth, r, e % kBlockWidth, t});
+        const int64_t lead = term_key[t].back();
+        const int32_t e = ent_index[lead / kCode] + (int32_t)(lead % kCode) - 1;
+        nz.push_back({e / kBlockWidth, row_tab[term_row[t]], e % kBlockWidth, t});
     }
-    const int32_t R = (int32_t)rparent.size();
-    plan.n_rows = R;
-    plan.n_hot = (int32_t)plan.hot_dim.size();
-    std::vector<int32_t> order(R), newid(R);
-    for (int32_t r = 0; r < R; ++r) order[r] = r;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return rlevel[a] < rlevel[b]; });
-    for (int32_t i = 0; i < R; ++i) newid[order[i]] = i;
-    plan.row_parent.resize(R);
-    plan.row_hslot.resize(R);
-    int maxlevel = 0;
-    for (int32_t i = 0; i < R; ++i) {
-        const int32_t old = order[i];
-        plan.row_parent[i] = old == 0 ? 0 : newid[rparent[old]];
-        plan.row_hslot[i] = old == 0 ? 0 : rhslot[old];
-        maxlevel = std::max(maxlevel, rlevel[old]);
-    }
-    plan.n_levels = maxlevel + 1;
-    plan.level_off.assign((size_t)plan.n_levels + 1, 0);
-    for (int32_t i = 0; i < R; ++i) plan.level_off[rlevel[order[i]] + 1]++;
-    for (int l = 0; l < plan.n_levels; ++l) plan.level_off[l + 1] += plan.level_off[l];
-
-    // ---- 8. block-sparse coefficient matrix and work items ----------------------------------------------------
-    for (Nz& z : nz) z.row = newid[z.row];
     std::sort(nz.begin(), nz.end(), [](const Nz& a, const Nz& b) {
         if (a.block != b.block) return a.block < b.block;
         if (a.row != b.row) return a.row < b.row;
         return a.lane < b.lane;
     });
+    auto block_flags = [&](int32_t b) {
+        int flags = kChunkHot | kChunkContig;
+        const int32_t e0 = b * kBlockWidth;
+        for (int i = 0; i < kBlockWidth; ++i) {
+            const int32_t e = e0 + i;
+            if (plan.ent_deg[e] > 0 && plan.ent_tab[e] == 0) flags &= ~kChunkHot;
+            if (plan.ent_deg[e] > 1 || plan.ent_dim[e] != plan.ent_dim[e0] + i) flags &= ~kChunkContig;
+        }
+        if (plan.ent_dim[e0] & 1) flags &= ~kChunkContig;
+        if (plan.ent_dim[e0] + kBlockWidth > d_in) flags &= ~kChunkContig;
+        if (flags & kChunkHot) flags &= ~kChunkContig;
+        return flags;
+    };
     struct Chunk {
-        int32_t block;
+        int32_t block, flags;
         std::vector<int32_t> rows;
         std::vector<double> coef;
     };
     std::vector<Chunk> chunks;
     for (size_t i = 0; i < nz.size();) {
         const int32_t b = nz[i].block;
-        // distinct rows of this block
         size_t j = i;
         std::vector<std::pair<int32_t, std::pair<size_t, size_t>>> rows;  // row -> [first, last)
         while (j < nz.size() && nz[j].block == b) {
@@ -410,12 +428,12 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             rows.push_back({nz[j].row, {j, k2}});
             j = k2;
         }
-        // split evenly into chunks of at most kChunkRows rows
         const size_t nr = rows.size(), nch = (nr + kChunkRows - 1) / kChunkRows;
-        for (size_t c = 0; c < nch; ++c) {
+        for (size_t c = 0; c < nch; ++c) {  // split evenly into chunks of at most kChunkRows rows
             const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
             Chunk ck;
             ck.block = b;
+            ck.flags = block_flags(b);
             ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
             for (size_t r = r0; r < r1; ++r) {
                 ck.rows.push_back(rows[r].first);
@@ -428,44 +446,82 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         }
         i = j;
     }
+    // Order: big (FP64-heavy) and small (streaming) items alternate, so that every warp of a CTA always has both kinds
+    // in flight (warp w takes items w, w + n_warps, ..).
     std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.rows.size() > b.rows.size(); });
+    {
+        std::vector<Chunk> mixed;
+        size_t lo = 0, hi = chunks.size();
+        const size_t group = 8;
+        bool front = true;
+        while (lo < hi) {
+            for (size_t g2 = 0; g2 < group && lo < hi; ++g2) mixed.push_back(std::move(front ? chunks[lo++] : chunks[--hi]));
+            front = !front;
+        }
+        chunks.swap(mixed);
+    }
     plan.n_chunks = (int32_t)chunks.size();
     plan.chunk_off.push_back(0);
     for (const Chunk& ck : chunks) {
         plan.chunk_block.push_back(ck.block);
+        plan.chunk_flags.push_back(ck.flags);
         plan.chunk_rows.insert(plan.chunk_rows.end(), ck.rows.begin(), ck.rows.end());
         plan.coef.insert(plan.coef.end(), ck.coef.begin(), ck.coef.end());
         plan.chunk_off.push_back((int32_t)plan.chunk_rows.size());
     }
     plan.padded_fma = (int64_t)plan.chunk_rows.size() * kBlockWidth;
+
+    // ---- 10. kernel-side packing: directory + one contiguous metadata record per work item ------------------------
+    plan.chunk_dir.resize((size_t)plan.n_chunks * 4);
+    plan.chunk_meta.assign((size_t)plan.n_chunks * kMetaInts, 0);
+    for (int32_t c = 0; c < plan.n_chunks; ++c) {
+        const int32_t e0 = plan.chunk_block[c] * kBlockWidth, r0 = plan.chunk_off[c], rows = plan.chunk_off[c + 1] - r0;
+        int32_t* dir = &plan.chunk_dir[(size_t)c * 4];
+        dir[0] = r0, dir[1] = rows, dir[2] = plan.chunk_flags[c], dir[3] = plan.ent_dim[e0];
+        int32_t* meta = &plan.chunk_meta[(size_t)c * kMetaInts];
+        double eta0[kBlockWidth];
+        for (int i = 0; i < kBlockWidth; ++i) {
+            meta[i] = plan.ent_tab[e0 + i];
+            meta[16 + i] = plan.ent_deg[e0 + i];
+            meta[32 + i] = plan.ent_eta[e0 + i];
+            meta[48 + i] = i < rows ? plan.chunk_rows[r0 + i] : 0;
+            eta0[i] = plan.ent_eta0[e0 + i];
+        }
+        std::memcpy(meta + 64, eta0, sizeof(eta0));
+    }
+    plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
+    for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
+    if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
     return "";
 }
 
 void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y) {
     const int64_t d_out = plan.d_out;
-    std::vector<double> pih((size_t)std::max(plan.n_hot, 1)), m((size_t)std::max(plan.n_rows, 1));
+    std::vector<double> tab((size_t)plan.n_tab);
     std::vector<double> acc((size_t)d_out);
+    auto pi = [&](const double* xp, int32_t e) {
+        double v = 1.0;
+        for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
+        return v;
+    };
     for (int64_t p = 0; p < N; ++p) {
         const double* xp = x + p * ldx;
-        for (int32_t h = 0; h < plan.n_hot; ++h) {
-            double v = 1.0;
-            for (int k = 0; k < plan.hot_deg[h]; ++k) v *= (xp[plan.hot_dim[h]] - plan.eta[plan.hot_eta[h] + k]);
-            pih[h] = v;
-        }
-        m[0] = 1.0;
-        for (int32_t r = 1; r < plan.n_rows; ++r) m[r] = m[plan.row_parent[r]] * pih[plan.row_hslot[r]];
+        tab[0] = 1.0;
+        for (size_t e = 0; e < plan.ent_dim.size(); ++e)
+            if (plan.ent_tab[e] > 0) tab[plan.ent_tab[e]] = pi(xp, (int32_t)e);
+        for (int32_t t = 1 + plan.n_hot; t < plan.n_tab; ++t)
+            tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot]] * tab[plan.tab_hot[t - 1 - plan.n_hot]];
         double* yp = y + p * d_out;
         for (int64_t o = 0; o < d_out; ++o) yp[o] = plan.c0[o];
         for (int32_t c = 0; c < plan.n_chunks; ++c) {
             const int32_t b = plan.chunk_block[c];
             for (int lane = 0; lane < kBlockWidth; ++lane) {
                 const int32_t e = b * kBlockWidth + lane;
-                double v = 1.0;
-                for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
+                const double v = (plan.chunk_flags[c] & kChunkHot) ? tab[plan.ent_tab[e]] : pi(xp, e);
                 std::fill(acc.begin(), acc.end(), 0.0);
                 for (int32_t i = plan.chunk_off[c]; i < plan.chunk_off[c + 1]; ++i)
                     for (int64_t o = 0; o < d_out; ++o)
-                        acc[o] = std::fma(plan.coef[((size_t)i * d_out + o) * kBlockWidth + lane], m[plan.chunk_rows[i]], acc[o]);
+                        acc[o] = std::fma(plan.coef[((size_t)i * d_out + o) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc[o]);
                 for (int64_t o = 0; o < d_out; ++o) yp[o] = std::fma(v, acc[o], yp[o]);
             }
         }
@@ -523,6 +579,7 @@ void smxh_plan_stats(void* p, int64_t* out) {
     auto* pl = static_cast<smx::FastPlan*>(p);
     int64_t v[11] = {pl->n_terms, pl->n_entries, pl->n_rows, pl->n_hot, pl->n_chunks, pl->padded_fma,
                      pl->n_levels, pl->nested ? 1 : 0, pl->n_summands, pl->w_raw, pl->w_pad};
+    (void)pl->n_tab;
     std::memcpy(out, v, sizeof(v));
 }
 // Verification aid, CPU tests only (see smx_plan.h).

@@ -44,37 +44,55 @@ struct GroupView {
 };
 
 constexpr int kBlockWidth = 16;    // entries per block: 4 lane-groups x 4 entries per lane
-constexpr int kChunkRows = 24;     // rows per work item
+constexpr int kChunkRows = 16;     // rows per work item
 constexpr int kMaxLevels = 16;
+
+constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
+
+// chunk flags
+constexpr int kChunkHot = 1;      // all 16 entries are hot: their basis values are rows of the value table
+constexpr int kChunkContig = 2;   // 16 degree-1 entries on consecutive columns of x starting at an even column
 
 struct FastPlan {
     int64_t d_in = 0, d_out = 0;
     bool nested = false;
     int64_t n_summands = 0, w_raw = 0, w_pad = 0, n_terms = 0;
 
-    // leading entries, sorted by (dimension, degree); padded to a multiple of kBlockWidth
+    // Leading entries (dimension, degree), sorted by dimension then degree; the *hot* entries (every entry of a
+    // dimension that occurs inside some hot part) form a prefix, padded with degree-0 dummies to a block boundary;
+    // cold blocks are padded so that they start at an even column of x.  Dummies have zero coefficients.
     int32_t n_entries = 0;               // real entries
-    std::vector<int32_t> ent_dim;        // column of x
-    std::vector<int32_t> ent_deg;        // a >= 1  (0 for padding lanes: pi = 1, coefficients are zero)
+    int32_t n_hot = 0;                   // hot prefix (real entries)
+    int32_t hot_dims = 0;                // the hot entries live on columns [0, hot_dims) of x
+    std::vector<int32_t> ent_dim;        // column of x (dummies: a valid column)
+    std::vector<int32_t> ent_deg;        // a >= 1, 0 for dummies (pi = 1)
     std::vector<int32_t> ent_eta;        // offset of the dimension's centres in `eta`
+    std::vector<int32_t> ent_tab;        // row of the value table holding pi_e (hot entries), 0 otherwise
+    std::vector<double> ent_eta0;        // first centre (pi_{j,1}(x) = x - eta0)
     std::vector<double> eta;             // centres, concatenated per dimension
 
-    // rows = distinct hot parts, sorted by level (number of pairs); row 0 is the empty product
-    int32_t n_rows = 0, n_levels = 0;
-    std::vector<int32_t> row_parent;     // m[r] = m[row_parent[r]] * pih[row_hslot[r]]
-    std::vector<int32_t> row_hslot;
-    std::vector<int32_t> level_off;      // rows of level l are [level_off[l], level_off[l+1])
-    int32_t n_hot = 0;                   // hot entries: (dim, deg) pairs that occur inside hot parts
-    std::vector<int32_t> hot_dim, hot_deg, hot_eta;
+    // Value table, one row of 32 points per index:  [0] = 1,  [1 .. n_hot] = pi of hot entry (index-1),
+    // [n_hot+1 ..) = products of >= 2 hot pairs ("rows" of level >= 2), each parent * hot:
+    int32_t n_tab = 1;
+    int32_t n_levels = 1;                // highest number of pairs in a hot part, plus one
+    std::vector<int32_t> tab_parent;     // for index >= n_hot+1 (level >= 2): table indices of the two factors
+    std::vector<int32_t> tab_hot;
+    std::vector<int32_t> level_off;      // table indices of level l (l >= 2) are [level_off[l], level_off[l+1])
 
     // work items: (entry block, slice of its row list); coefficients [row slot][d_out][kBlockWidth]
     int32_t n_chunks = 0;
     std::vector<int32_t> chunk_block;
+    std::vector<int32_t> chunk_flags;
     std::vector<int32_t> chunk_off;      // size n_chunks+1, offsets into chunk_rows / coefficient row slots
-    std::vector<int32_t> chunk_rows;
+    std::vector<int32_t> chunk_rows;     // value-table index of every row slot
     std::vector<double> coef;
+    // the same information packed for the kernel: one directory entry and one metadata record per work item
+    std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags, first column of x
+    std::vector<int32_t> chunk_meta;     // kMetaInts ints per item: tab[16], deg[16], eta offset[16], row index[16], eta0[16] (doubles)
+    std::vector<int32_t> hot_off;        // prefix sums of the degrees of the hot dimensions, size hot_dims + 1
     std::vector<double> c0;              // (d_out) constant term, includes the offset
     int64_t padded_fma = 0;              // row slots * kBlockWidth
+    int32_t n_rows = 0;                  // distinct hot parts (statistics)
 };
 
 // Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).

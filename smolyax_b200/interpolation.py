@@ -264,6 +264,10 @@ class SmolyakBarycentricInterpolator:
         self._n_inputs = x.shape[0]
         return x, kind
 
+    def _ldx(self, x) -> int:
+        """Row pitch in elements (a single row may carry an arbitrary stride on its size-1 axis)."""
+        return int(x.stride(0)) if x.shape[0] > 1 else self._d_in
+
     @staticmethod
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -282,11 +286,11 @@ class SmolyakBarycentricInterpolator:
         with torch.cuda.device(self._device):
             if kind == "cuda":
                 y = torch.empty((n_points, self._d_out), dtype=torch.float64, device=x.device)
-                _lib.check(lib.smx_eval(self._handle, x.data_ptr(), n_points, x.stride(0), y.data_ptr(), self._stream()), "smx_eval")
+                _lib.check(lib.smx_eval(self._handle, x.data_ptr(), n_points, self._ldx(x), y.data_ptr(), self._stream()), "smx_eval")
                 return y
             if kind == "torch_cpu":
                 y = torch.empty((n_points, self._d_out), dtype=torch.float64, pin_memory=x.is_pinned())
-                _lib.check(lib.smx_eval_host(self._handle, x.data_ptr(), n_points, x.stride(0), y.data_ptr(), 0), "smx_eval_host")
+                _lib.check(lib.smx_eval_host(self._handle, x.data_ptr(), n_points, self._ldx(x), y.data_ptr(), 0), "smx_eval_host")
                 return y
             y = np.empty((n_points, self._d_out))
             _lib.check(lib.smx_eval_host(self._handle, x.ctypes.data, n_points, x.shape[1], y.ctypes.data, 0), "smx_eval_host")
@@ -301,7 +305,7 @@ class SmolyakBarycentricInterpolator:
         with torch.cuda.device(self._device):
             xd = x if kind == "cuda" else (x.cuda() if kind == "torch_cpu" else torch.from_numpy(x).cuda())
             J = torch.empty((n_points, self._d_out, self._d_in), dtype=torch.float64, device=xd.device)
-            _lib.check(_lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, xd.stride(0), J.data_ptr(), self._stream()),
+            _lib.check(_lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, self._ldx(xd), J.data_ptr(), self._stream()),
                        "smx_gradient")
             if kind == "cuda":
                 return J
