@@ -81,7 +81,8 @@ struct FastDevice {
     double* c0 = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
-    int warps = 4;  // warps per CTA of the evaluation kernel (4: two CTAs per SM, 8: one)
+    int warps = 4;      // warps per CTA of the cp.async kernel (4: two CTAs per SM, 8: one)
+    int tma_warps = 0;  // warps per CTA of the TMA kernel (0: not available for this plan)
 };
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);

@@ -21,47 +21,10 @@
 #include <algorithm>
 #include <cstddef>
 
-#include "smx_common.cuh"
+#include "smx_fast_common.cuh"
 
 namespace smx {
 namespace {
-
-constexpr int kTile = 32;  // points per tile
-static_assert(kBlockWidth == 16, "lane mapping below assumes 16 entries per block");
-static_assert(kChunkRows == 16, "the metadata record holds 16 row indices");
-
-struct FastArgs {
-    const int32_t* ent_dim;  // only read for the (rare) cold blocks whose columns are not contiguous
-    const double* eta;
-    const int2* tab_pairs;   // value-table rows of level >= 2: (parent row, hot row)
-    const int32_t* hot_off;
-    const int4* chunk_dir;   // per work item: first row slot, rows, flags | block << 4, first column of x
-    const int32_t* chunk_meta;
-    const double* coef;
-    const double* c0;
-    long long N, ldx, d_out, num_tiles;
-    int n_hot, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
-    int x_vec_ok;  // x is 16-byte aligned and ldx is even: contiguous blocks may be staged with 16-byte copies
-    int level_off[kMaxLevels + 2];
-};
-
-// One work item as the kernel sees it in shared memory: metadata record (smx_plan.h, kMetaInts) + coefficient rows.
-struct alignas(16) ItemBuffer {
-    int tab[16];      // value-table row of each entry (hot blocks)
-    int deg[16];      // degree of each entry (0: dummy)
-    int etaoff[16];   // offset of the entry's centres in `eta`
-    int ridx[16];     // value-table row of each coefficient row
-    double eta0[16];  // first centre of each entry
-    double coef[kChunkRows * kBlockWidth];
-};
-static_assert(offsetof(ItemBuffer, coef) == kMetaInts * 4, "metadata record layout");
-
-// Per-warp staging area, filled with cp.async one item ahead of its use: the x tile of the item (32 points x 16
-// entries; consumed into registers at the start of the item, so one buffer is enough) and two item buffers.
-struct alignas(16) WarpStage {
-    double xs[kTile * kBlockWidth];
-    ItemBuffer item[2];
-};
 
 // position of tile point t (= 4 * group + pp) inside a 32-double row of the value table: the two halves of a lane's
 // four points are 128 bytes apart so that one LDS.128 of the 8 point-groups reads 128 contiguous bytes
@@ -88,12 +51,12 @@ __device__ __forceinline__ void stage_item(const FastArgs& a, const double* __re
         cp_async16(reinterpret_cast<int*>(&st.item[buf]) + 4 * lane, a.chunk_meta + (size_t)c * kMetaInts + 4 * lane);
     for (int id = lane; id < rows * 8; id += 32) {
         const int r = id >> 3, cc = id & 7;
-        cp_async16(&st.item[buf].coef[r * kBlockWidth + 2 * cc], a.coef + ((size_t)(r0 + r) * a.d_out + o) * kBlockWidth + 2 * cc);
+        cp_async16(&st.item[buf].coef[r * kBlockWidth + 2 * cc], a.coef + ((size_t)r0 * a.d_out + (size_t)o * rows + r) * kBlockWidth + 2 * cc);
     }
     if (!(flags & kChunkHot)) {
         // x tile: row `row` of the tile at 128-byte pitch; its 16-byte pieces are XOR-swizzled with bit 2 of the row so
         // that the readers (lane = 4 * group + entry-group, row = 4 * group + pp) do not collide on banks
-        if ((flags & kChunkContig) && a.x_vec_ok) {
+        if ((flags & kChunkInside) && a.x_vec_ok) {
             const int dim0 = dir.w;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -349,14 +312,24 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
     if ((rc = upload(plan.chunk_meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
-    if ((rc = upload(plan.coef, &dev.coef, dev.bytes))) return rc;
+    {   // device layout of the coefficients: per work item [output][row][16], so that one (item, output) is contiguous
+        std::vector<double> packed(plan.coef.size());
+        for (int32_t c = 0; c < plan.n_chunks; ++c) {
+            const size_t r0 = plan.chunk_off[c], rows = plan.chunk_off[c + 1] - r0, dout = (size_t)plan.d_out;
+            for (size_t r = 0; r < rows; ++r)
+                for (size_t o = 0; o < dout; ++o)
+                    std::copy_n(&plan.coef[((r0 + r) * dout + o) * kBlockWidth], kBlockWidth,
+                                &packed[(r0 * dout + o * rows + r) * kBlockWidth]);
+        }
+        if ((rc = upload(packed, &dev.coef, dev.bytes))) return rc;
+    }
     if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
     const size_t smem = fast_smem_bytes(dev, dev.warps);
     if (dev.warps == 4)
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return SMX_OK;
+    return fast_tma_prepare(dev);
 }
 
 void fast_free(FastDevice& d) {
@@ -368,7 +341,22 @@ void fast_free(FastDevice& d) {
 
 int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
     if (N == 0) return SMX_OK;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 1) == 0;
+    if (aligned && d.tma_warps > 0) return fast_eval_tma(d, x, N, ldx, y, st);
     FastArgs a;
+    fill_fast_args(d, x, N, ldx, a);
+    const size_t smem = fast_smem_bytes(d, d.warps);
+    const int per_sm = d.warps == 4 ? 2 : 1;
+    const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * per_sm);
+    if (d.warps == 4)
+        fast_eval_kernel<4><<<(unsigned)grid, 128, smem, st>>>(a, x, y);
+    else
+        fast_eval_kernel<8><<<(unsigned)grid, 256, smem, st>>>(a, x, y);
+    SMX_LAUNCH_CHECK("fast_eval_kernel");
+    return SMX_OK;
+}
+
+void fill_fast_args(const FastDevice& d, const double* x, int64_t N, int64_t ldx, FastArgs& a) {
     a.ent_dim = d.ent_dim;
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
@@ -389,15 +377,6 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.n_pairs = d.n_pairs;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 1) == 0) ? 1 : 0;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
-    const size_t smem = fast_smem_bytes(d, d.warps);
-    const int per_sm = d.warps == 4 ? 2 : 1;
-    const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * per_sm);
-    if (d.warps == 4)
-        fast_eval_kernel<4><<<(unsigned)grid, 128, smem, st>>>(a, x, y);
-    else
-        fast_eval_kernel<8><<<(unsigned)grid, 256, smem, st>>>(a, x, y);
-    SMX_LAUNCH_CHECK("fast_eval_kernel");
-    return SMX_OK;
 }
 
 }  // namespace smx

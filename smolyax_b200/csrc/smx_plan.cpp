@@ -325,9 +325,14 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         term_row[t] = id;
     }
     plan.n_rows = (int32_t)row_key.size();
-    plan.hot_dims = hot_dim_max + 1;
 
-    // ---- 7. leading entries: hot prefix, block padding, even-aligned cold blocks --------------------------------
+    // ---- 7. leading entries: hot prefix, then cold blocks = 16 consecutive columns of x from an even column -----------
+    // The hot prefix holds every entry of the dimensions up to the last one that occurs inside a hot part or has a
+    // degree above 1; beyond it every dimension has at most the entry (dim, 1), so a cold block is a contiguous tile
+    // of x (dummy entries with zero coefficients fill unused columns).
+    for (int64_t d = 0; d < d_in; ++d)
+        if (maxdeg[d] >= 2) hot_dim_max = std::max(hot_dim_max, (int)d);
+    plan.hot_dims = hot_dim_max + 1;
     std::vector<int32_t> ent_index((size_t)d_in, -1);  // entry of (dim, 1); (dim, a) is ent_index[dim] + a - 1
     auto push_entry = [&](int32_t dim, int32_t deg, int32_t tab) {
         plan.ent_dim.push_back(dim);
@@ -336,23 +341,29 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         plan.ent_tab.push_back(tab);
         plan.ent_eta0.push_back(maxdeg[dim] > 0 ? plan.eta[eta_off[dim]] : 0.0);
     };
-    auto pad_block = [&]() {
-        while (plan.ent_dim.size() % kBlockWidth) push_entry(0, 0, 0);
-    };
-    for (int64_t d = 0; d < d_in; ++d) {
+    for (int64_t d = 0; d <= hot_dim_max; ++d) {
         if (maxdeg[d] == 0) continue;
-        const bool hot = d <= hot_dim_max;
-        // a cold block that would start on an odd column gets the column before it as a dummy first entry
-        if (!hot && plan.ent_dim.size() % kBlockWidth == 0 && (d & 1)) push_entry((int32_t)d - 1, 0, 0);
         ent_index[d] = (int32_t)plan.ent_dim.size();
         for (int a = 1; a <= maxdeg[d]; ++a) {
-            push_entry((int32_t)d, a, hot ? plan.n_hot + 1 : 0);
-            if (hot) ++plan.n_hot;
+            push_entry((int32_t)d, a, ++plan.n_hot);
             ++plan.n_entries;
         }
-        if (hot && (d == hot_dim_max)) pad_block();  // cold entries start on a block boundary
     }
-    pad_block();
+    while (plan.ent_dim.size() % kBlockWidth) push_entry(0, 0, 0);  // cold entries start on a block boundary
+    for (int64_t next = hot_dim_max + 1; next < d_in;) {
+        while (next < d_in && maxdeg[next] == 0) ++next;  // skip columns nobody uses
+        if (next >= d_in) break;
+        const int64_t col0 = next & ~(int64_t)1;
+        for (int64_t col = col0; col < col0 + kBlockWidth; ++col) {
+            const bool real = col >= next && col < d_in && maxdeg[col] == 1;
+            if (real) {
+                ent_index[col] = (int32_t)plan.ent_dim.size();
+                ++plan.n_entries;
+            }
+            push_entry((int32_t)std::min<int64_t>(col, d_in - 1), real ? 1 : 0, 0);
+        }
+        next = col0 + kBlockWidth;
+    }
     // hot entry h (in entry order) sits in table row 1 + h; map (dim, deg) code -> table row
     std::unordered_map<int64_t, int32_t> hot_tab;
     for (size_t e = 0; e < plan.ent_dim.size(); ++e)
@@ -405,11 +416,12 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         for (int i = 0; i < kBlockWidth; ++i) {
             const int32_t e = e0 + i;
             if (plan.ent_deg[e] > 0 && plan.ent_tab[e] == 0) flags &= ~kChunkHot;
-            if (plan.ent_deg[e] > 1 || plan.ent_dim[e] != plan.ent_dim[e0] + i) flags &= ~kChunkContig;
+            if (plan.ent_deg[e] > 1) flags &= ~kChunkContig;
+            if (plan.ent_dim[e] != std::min<int64_t>(plan.ent_dim[e0] + i, d_in - 1)) flags &= ~kChunkContig;
         }
         if (plan.ent_dim[e0] & 1) flags &= ~kChunkContig;
-        if (plan.ent_dim[e0] + kBlockWidth > d_in) flags &= ~kChunkContig;
         if (flags & kChunkHot) flags &= ~kChunkContig;
+        if ((flags & kChunkContig) && plan.ent_dim[e0] + kBlockWidth <= d_in) flags |= kChunkInside;
         return flags;
     };
     struct Chunk {

@@ -52,6 +52,7 @@ constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
 // chunk flags
 constexpr int kChunkHot = 1;      // all 16 entries are hot: their basis values are rows of the value table
 constexpr int kChunkContig = 2;   // 16 degree-1 entries on consecutive columns of x starting at an even column
+constexpr int kChunkInside = 4;   // .. and the 16 columns all exist (first column + 16 <= d_in)
 
 struct FastPlan {
     int64_t d_in = 0, d_out = 0;

@@ -150,6 +150,13 @@ def test_strided_input_and_c_abi_directly():
     assert np.array_equal(out.cpu().numpy(), y)
     assert np.array_equal(ip(wide[:, :37]).cpu().numpy(), y)  # non-contiguous view, stride(0) = 48
     assert _lib.lib.smx_eval(ip._handle, wide.data_ptr(), 10, 5, out.data_ptr(), stream) == 1  # ldx < d_in
+    # rows that are not 16-byte aligned (odd pitch) take the cp.async kernel instead of the TMA kernel: same values
+    odd = torch.zeros((1001, 49), dtype=torch.float64, device="cuda")
+    odd[:, :37] = torch.from_numpy(x).cuda()
+    assert np.allclose(ip(odd[:, :37]).cpu().numpy(), y, rtol=1e-13, atol=1e-14)
+    shifted = torch.zeros(1001 * 48 + 1, dtype=torch.float64, device="cuda")[1:].view(1001, 48)  # base not 16-byte aligned
+    shifted[:, :37] = torch.from_numpy(x).cuda()
+    assert np.allclose(ip(shifted[:, :37]).cpu().numpy(), y, rtol=1e-13, atol=1e-14)
     before = _lib.lib.smx_launch_count()
     ip(wide[:, :37])
     assert _lib.lib.smx_launch_count() == before + 1  # one fused kernel per call
