@@ -71,7 +71,6 @@ struct FastDevice {
     int64_t d_in = 0, d_out = 0;
     int32_t n_tab = 1, n_hot = 0, n_levels = 1, n_chunks = 0, hot_dims = 0, n_pairs = 0;
     int32_t level_off[kMaxLevels + 2] = {0};
-    int32_t* ent_dim = nullptr;
     double* eta = nullptr;
     int32_t* tab_pairs = nullptr;
     int32_t* hot_off = nullptr;
@@ -81,8 +80,7 @@ struct FastDevice {
     double* c0 = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
-    int warps = 4;      // warps per CTA of the cp.async kernel (4: two CTAs per SM, 8: one)
-    int tma_warps = 0;  // warps per CTA of the TMA kernel (0: not available for this plan)
+    int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
 };
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);

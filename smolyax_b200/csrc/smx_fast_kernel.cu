@@ -1,0 +1,343 @@
+// Fast evaluation path (K1): fused 1-D basis + block-sparse Kronecker contraction on the hierarchical layout of
+// smx_plan.h.  Replaces the whole of reference interpolation.py:281-302 (python loop over groups and summand batches
+// around jit(vmap(barycentric.evaluate_tensor_product_interpolant))) by ONE persistent kernel:
+//
+//   I(x_p) = c_0 + sum_{e=(j,a)} pi_e(x_pj) * sum_r C[r][e] * m_r(x_p)
+//
+// One CTA works on one tile of 32 evaluation points at a time (12 or 8 warps and one CTA per SM, or 4 warps and two).
+//   * prologue : the CTA fills the value table in shared memory (one row of 32 points per index, pitch kTabPitch):
+//                row 0 = 1, then the 1-D basis values pi_e(x_p) of the hot entries (lane = point, running product over
+//                the Newton centres; the hot coordinates of the NEXT tile are already in registers, loaded during the
+//                previous main loop), then level by level the products of two and more hot pairs.
+//   * main     : warp w takes the work items (block of 16 leading entries x <= 16 rows) w, w + NW, ..  One item ahead
+//                of its use, one lane stages the item with the TMA: the 32-point x 16-column tile of x of a cold block
+//                is ONE cp.async.bulk.tensor.2d (128-byte swizzle; rows beyond N and columns beyond d_in are
+//                zero-filled by the hardware; every coordinate of x is read from HBM exactly once), the item's
+//                metadata record and its packed coefficients are two cp.async.bulk copies; all complete on an mbarrier.
+//                The contraction  acc[p][e] = sum_r m_r(x_p) C[r][e]  runs on the FP64 tensor path:
+//                mma.sync.m8n8k4.f64 with A = value-table rows (points x rows), B = coefficients (rows x entries),
+//                32 points x 16 entries x 4 rows per k-step = 8 DMMA; accumulators stay in registers.
+//                Then tot[p] += sum_e pi_e(x_p) * acc[p][e] with pi_e formed in registers from the staged x tile
+//                (or read from the value table for hot blocks).
+//   * epilogue : shuffle-reduce over the 4 lanes that share a point, fixed-order sum over the warps, store y.
+// Static work assignment, fixed summation order: results are bit-reproducible run to run.
+//
+// Lane mapping (DMMA fragment layout): gid = lane >> 2, tig = lane & 3.  The lane owns points gid + 8 i (i = 0..3)
+// and entries 4 tig + 2 j + {0, 1} (j = 0..1) of the block; accumulator tile (i, j) is the 8 x 8 DMMA tile of points
+// 8 i .. 8 i + 7 and the 8 entries { 4 (n >> 1) + 2 j + (n & 1) : n = 0..7 }.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "smx_fast_common.cuh"
+
+namespace smx {
+namespace {
+
+constexpr int kXTileBytes = kTile * kBlockWidth * 8;  // 4096
+constexpr int kHotRegs = 8;                           // hot coordinates per lane kept in registers for the next tile
+
+struct alignas(1024) Stage {
+    double xs[kTile * kBlockWidth];  // TMA destination, 128-byte swizzle => 1024-byte alignment
+    ItemBuffer item[2];
+    unsigned long long bar[2];       // mbarriers: item buffer b (and the x tile that travels with that item)
+};
+
+// tile point t = gid + 8 * i  ->  position inside a value-table row: points (gid, gid + 8) and (gid + 16, gid + 24)
+// are adjacent pairs, the second pair 16 doubles after the first (two LDS.128 fetch a lane's four A-fragment values)
+__device__ __forceinline__ int t_slot(int t) { return ((t >> 4) & 1) * 16 + (t & 7) * 2 + ((t >> 3) & 1); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// D (8x8, fp64) += A (8x4, row) * B (4x8, col): one value of A and B per lane, two of D
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
+__device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, Stage& st, int buf, int c, const int4 dir,
+                                           long long o, long long p0) {
+    const int ksteps = (dir.y + 3) >> 2;
+    const unsigned coef_bytes = (unsigned)ksteps * kKStepDoubles * 8;
+    const bool cold = !(dir.z & kChunkHot);
+    mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
+    bulk_copy(&st.item[buf], a.chunk_meta + (size_t)c * kMetaInts, kMetaInts * 4, &st.bar[buf]);
+    bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);
+    if (cold) tma_load_2d(st.xs, xmap, dir.w, (int)p0, &st.bar[buf]);
+}
+
+template <int NW, int CTAS>
+__global__ void __launch_bounds__(NW * 32, CTAS)
+fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
+    constexpr int kThreads = NW * 32;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte aligned carve-up (the launch adds 1 KiB of slack)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    Stage* stages = reinterpret_cast<Stage*>(base);                              // [NW]
+    double* tab = reinterpret_cast<double*>(stages + NW);                         // [n_tab][kTabPitch] value table
+    double* ypart = tab + (size_t)a.n_tab * kTabPitch;                            // [NW][32]
+    int4* s_dir = reinterpret_cast<int4*>(ypart + NW * kTile);                    // [n_chunks]
+    double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);                // [n_hot] centres of the hot dimensions
+    int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // [n_pairs]
+    int* s_hot_off = reinterpret_cast<int*>(s_pairs + a.n_pairs);                 // [hot_dims + 1]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tig = lane & 3, gid = lane >> 2;
+    Stage& st = stages[warp];
+
+    // ---- once per CTA: small tables to shared memory, mbarriers --------------------------------------------------------
+    for (int i = tid; i < a.n_chunks; i += kThreads) s_dir[i] = __ldg(a.chunk_dir + i);
+    for (int i = tid; i < a.n_hot; i += kThreads) s_eta[i] = __ldg(a.eta + i);
+    for (int i = tid; i < a.n_pairs; i += kThreads) s_pairs[i] = __ldg(a.tab_pairs + i);
+    for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
+    if (lane == 0) {
+        mbar_init(&st.bar[0], 1);
+        mbar_init(&st.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // hot coordinates of this lane's point: dimension warp + NW * u for u < kHotRegs live in registers, loaded one tile ahead
+    double xhot[kHotRegs];
+    auto load_hot = [&](long long tile_p0) {
+        const double* xrow = x + min(tile_p0 + lane, a.N - 1) * a.ldx;
+#pragma unroll
+        for (int u = 0; u < kHotRegs; ++u) xhot[u] = (warp + NW * u < a.hot_dims) ? __ldg(xrow + warp + NW * u) : 0.0;
+    };
+    if ((long long)blockIdx.x < a.num_tiles) load_hot((long long)blockIdx.x * kTile);
+    __syncthreads();
+
+    unsigned k_item = 0;  // items this warp has consumed so far: buffer = k & 1, phase parity = (k >> 1) & 1
+
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const long long p0 = tile * kTile;
+
+        // ---- prologue: value table = 1 | 1-D basis values of the hot entries | products of hot pairs, level by level ----
+        if (tid < kTile) tab[tid] = 1.0;
+        {
+            const int slot = t_slot(lane);
+            auto hot_dim = [&](int d, double xv) {
+                double v = 1.0;
+                for (int k = s_hot_off[d]; k < s_hot_off[d + 1]; ++k) {
+                    v *= (xv - s_eta[k]);
+                    tab[(1 + k) * kTabPitch + slot] = v;
+                }
+            };
+#pragma unroll
+            for (int u = 0; u < kHotRegs; ++u)
+                if (warp + NW * u < a.hot_dims) hot_dim(warp + NW * u, xhot[u]);
+            if (a.hot_dims > NW * kHotRegs) {  // more hot dimensions than the register prefetch covers: load them now
+                const double* xrow = x + min(p0 + lane, a.N - 1) * a.ldx;
+                for (int d = warp + NW * kHotRegs; d < a.hot_dims; d += NW) hot_dim(d, __ldg(xrow + d));
+            }
+        }
+        __syncthreads();
+        for (int l = 2; l < a.n_levels; ++l) {
+            const int t_begin = a.level_off[l], count = (a.level_off[l + 1] - t_begin) * kTile;
+            for (int idx = tid; idx < count; idx += kThreads) {
+                const int ti = t_begin + (idx >> 5), s = idx & 31;
+                const int2 pr = s_pairs[ti - 1 - a.n_hot];
+                tab[ti * kTabPitch + s] = tab[pr.x * kTabPitch + s] * tab[pr.y * kTabPitch + s];
+            }
+            __syncthreads();
+        }
+        if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);  // lands during the main loop
+
+        // ---- main: block-sparse contraction, one output at a time -------------------------------------------------------
+        for (long long o = 0; o < a.d_out; ++o) {
+            double tot[4] = {0.0, 0.0, 0.0, 0.0};
+            if (warp < a.n_chunks && lane == 0) stage_item(a, &xmap, st, k_item & 1, warp, s_dir[warp], o, p0);
+            for (int c = warp; c < a.n_chunks; c += NW, ++k_item) {
+                const int buf = k_item & 1;
+                const int4 dir = s_dir[c];
+                const ItemBuffer& ib = st.item[buf];
+                mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
+
+                // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
+                double v[4][4];
+                if (dir.z & kChunkHot) {
+                    const int4 t4 = *reinterpret_cast<const int4*>(ib.tab + 4 * tig);
+                    const int tabs[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double* tr = tab + tabs[e] * kTabPitch + 2 * gid;
+                        const double2 lo = *reinterpret_cast<const double2*>(tr);
+                        const double2 hi = *reinterpret_cast<const double2*>(tr + 16);
+                        v[0][e] = lo.x, v[1][e] = lo.y, v[2][e] = hi.x, v[3][e] = hi.y;
+                    }
+                } else {
+                    // 128-byte swizzle: 16-byte piece j of row r sits at piece j ^ (r & 7); r = gid + 8 i => r & 7 = gid
+                    const double2 ea = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig);
+                    const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double* xr = st.xs + (gid + 8 * i) * kBlockWidth;
+                        const double2 lo = *reinterpret_cast<const double2*>(xr + (((2 * tig) ^ gid) << 1));
+                        const double2 hi = *reinterpret_cast<const double2*>(xr + (((2 * tig + 1) ^ gid) << 1));
+                        v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
+                    }
+                }
+                __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
+                if (c + NW < a.n_chunks && lane == 0) stage_item(a, &xmap, st, buf ^ 1, c + NW, s_dir[c + NW], o, p0);
+
+                // acc[i][j] (8 x 8 tiles) += A (value-table rows of this k-step) * B (packed coefficients)
+                double acc[4][2][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                const int ksteps = (dir.y + 3) >> 2;
+#pragma unroll 2
+                for (int s = 0; s < ksteps; ++s) {
+                    const double* ap = tab + ib.ridx[4 * s + tig] * kTabPitch + 2 * gid;
+                    const double2 a01 = *reinterpret_cast<const double2*>(ap);
+                    const double2 a23 = *reinterpret_cast<const double2*>(ap + 16);
+                    const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
+                    const double af[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dmma(acc[i][0], af[i], b.x);
+                        dmma(acc[i][1], af[i], b.y);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    tot[i] = fma(v[i][0], acc[i][0][0], tot[i]);
+                    tot[i] = fma(v[i][1], acc[i][0][1], tot[i]);
+                    tot[i] = fma(v[i][2], acc[i][1][0], tot[i]);
+                    tot[i] = fma(v[i][3], acc[i][1][1], tot[i]);
+                }
+            }
+            // ---- epilogue: reduce over the 4 lanes that share a point, then over the warps in fixed order ---------------
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tot[i] += __shfl_xor_sync(0xffffffffu, tot[i], 1);
+                tot[i] += __shfl_xor_sync(0xffffffffu, tot[i], 2);
+            }
+            if (tig == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ypart[warp * kTile + gid + 8 * i] = tot[i];
+            }
+            __syncthreads();
+            if (tid < kTile && p0 + tid < a.N) {
+                double s = __ldg(a.c0 + o);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += ypart[w * kTile + tid];
+                y[(p0 + tid) * a.d_out + o] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+size_t smem_bytes(const FastDevice& d, int nw) {
+    return 1024 + (size_t)nw * sizeof(Stage) + ((size_t)d.n_tab * kTabPitch + (size_t)nw * kTile + (size_t)d.n_hot) * sizeof(double) +
+           (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1) * sizeof(int) + 16;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library links no libcuda, so it still loads
+// (and reports "no device") on a machine without a driver.
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int NW, int CTAS>
+int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
+    const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * CTAS);
+    fast_eval_kernel<NW, CTAS><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
+    SMX_LAUNCH_CHECK("fast_eval_kernel");
+    return SMX_OK;
+}
+
+}  // namespace
+
+// Chooses the CTA shape for this plan and opts into the shared memory it needs.
+int fast_kernel_prepare(FastDevice& d) {
+    if (encode_tiled() == nullptr) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    int device = 0, smem_optin = 0, smem_sm = 0;
+    SMX_CUDA(cudaGetDevice(&device));
+    SMX_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    int want = 0;
+    if (const char* env = std::getenv("SMX_FAST_WARPS")) want = std::atoi(env);  // tuning knob: 4, 8 or 12
+    const bool fits4 = 2 * (smem_bytes(d, 4) + 1024) <= (size_t)smem_sm;
+    const bool fits8 = smem_bytes(d, 8) <= (size_t)smem_optin;
+    const bool fits12 = smem_bytes(d, 12) <= (size_t)smem_optin;
+    d.warps = 0;
+    if (want == 12 && fits12) d.warps = 12;
+    else if (want == 8 && fits8) d.warps = 8;
+    else if (want == 4 && fits4) d.warps = 4;
+    else if (fits12) d.warps = 12;
+    else if (fits8) d.warps = 8;
+    else if (fits4) d.warps = 4;
+    if (d.warps == 0) return fail(SMX_ERR_UNSUPPORTED, "value table does not fit in shared memory");
+    if (d.warps == 4)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 4)));
+    if (d.warps == 8)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 8)));
+    if (d.warps == 12)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 12)));
+    return SMX_OK;
+}
+
+int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st) {
+    // tensor map of x: (N rows) x (d_in columns) fp64, row pitch ldx * 8 bytes; box = 16 columns x 32 rows
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)d.d_in, (cuuint64_t)a.N};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.ldx * sizeof(double)};
+    const cuuint32_t box[2] = {kBlockWidth, kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult res = encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
+    if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
+    if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
+    return launch<12, 1>(map, a, d, x, y, st);
+}
+
+}  // namespace smx

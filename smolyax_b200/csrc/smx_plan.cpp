@@ -447,12 +447,23 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             ck.block = b;
             ck.flags = block_flags(b);
             ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
-            for (size_t r = r0; r < r1; ++r) {
+            // order the rows so that every group of four (one DMMA k-step) has four different table-row residues
+            // modulo 4 as long as the item has them: with kTabPitch that makes the A-fragment loads conflict free
+            std::vector<size_t> order;
+            {
+                std::vector<std::vector<size_t>> cls(4);
+                for (size_t r = r0; r < r1; ++r) cls[rows[r].first & 3].push_back(r);
+                size_t taken[4] = {0, 0, 0, 0};
+                while (order.size() < r1 - r0)
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        if (taken[k4] < cls[k4].size()) order.push_back(cls[k4][taken[k4]++]);
+            }
+            for (size_t pos = 0; pos < order.size(); ++pos) {
+                const size_t r = order[pos];
                 ck.rows.push_back(rows[r].first);
                 for (size_t q = rows[r].second.first; q < rows[r].second.second; ++q)
                     for (int64_t o = 0; o < d_out; ++o)
-                        ck.coef[((r - r0) * (size_t)d_out + o) * kBlockWidth + nz[q].lane] =
-                            (double)C[(size_t)nz[q].term * d_out + o];
+                        ck.coef[(pos * (size_t)d_out + o) * kBlockWidth + nz[q].lane] = (double)C[(size_t)nz[q].term * d_out + o];
             }
             chunks.push_back(std::move(ck));
         }

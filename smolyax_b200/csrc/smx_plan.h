@@ -48,6 +48,8 @@ constexpr int kChunkRows = 16;     // rows per work item
 constexpr int kMaxLevels = 16;
 
 constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
+constexpr int kTabPitch = 36;      // doubles per value-table row in shared memory (32 points + 32 bytes of skew:
+                                   // rows r, r' with r != r' (mod 4) never share a bank in the DMMA A-fragment loads)
 
 // chunk flags
 constexpr int kChunkHot = 1;      // all 16 entries are hot: their basis values are rows of the value table
