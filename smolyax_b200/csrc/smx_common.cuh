@@ -69,7 +69,8 @@ int device_basis(const double* x, int64_t N, const double* xi, const double* w, 
 // fast path (smx_fast.cu)
 struct FastDevice {
     int64_t d_in = 0, d_out = 0;
-    int32_t n_tab = 1, n_hot = 0, n_levels = 1, n_chunks = 0, hot_dims = 0, n_pairs = 0;
+    int32_t n_tab = 1, n_hot = 0, n_hot_rows = 0, n_levels = 1, n_chunks = 0, hot_dims = 0, n_pairs = 0;
+    int32_t warp_off[17] = {0};  // per-warp item lists (balanced at upload for the chosen CTA shape)
     int32_t level_off[kMaxLevels + 2] = {0};
     double* eta = nullptr;
     int32_t* tab_pairs = nullptr;

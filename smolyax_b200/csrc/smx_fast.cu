@@ -50,6 +50,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     dev.d_out = plan.d_out;
     dev.n_tab = plan.n_tab;
     dev.n_hot = plan.n_hot;
+    dev.n_hot_rows = plan.n_hot_rows;
     dev.n_levels = plan.n_levels;
     dev.n_chunks = plan.n_chunks;
     dev.hot_dims = plan.hot_dims;
@@ -68,15 +69,46 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     std::vector<double> packed;
     std::vector<int32_t> kstep_off;
     pack_coefficients(plan, packed, kstep_off);
-    std::vector<int32_t> dir(plan.chunk_dir);
-    for (int32_t c = 0; c < plan.n_chunks; ++c) dir[(size_t)c * 4] = kstep_off[c];
+    // Balanced static schedule for the chosen CTA shape: longest-processing-time assignment of the work items to the
+    // warps (cost ~ fixed part + k-steps), then every warp alternates big and small items so that tensor-heavy and
+    // streaming items are always in flight together.  Directory and metadata records are stored in that order.
+    std::vector<int32_t> dir((size_t)plan.n_chunks * 4), meta((size_t)plan.n_chunks * kMetaInts);
+    {
+        const int nw = dev.warps;
+        auto cost = [&](int32_t c) { return 2.0 + (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4); };
+        std::vector<int32_t> by_cost((size_t)plan.n_chunks);
+        for (int32_t c = 0; c < plan.n_chunks; ++c) by_cost[c] = c;
+        std::stable_sort(by_cost.begin(), by_cost.end(), [&](int32_t x1, int32_t x2) { return cost(x1) > cost(x2); });
+        std::vector<std::vector<int32_t>> lists((size_t)nw);
+        std::vector<double> load((size_t)nw, 0.0);
+        for (int32_t c : by_cost) {
+            const size_t w = std::min_element(load.begin(), load.end()) - load.begin();
+            lists[w].push_back(c);
+            load[w] += cost(c);
+        }
+        size_t pos = 0;
+        for (int w = 0; w < nw; ++w) {
+            dev.warp_off[w] = (int32_t)pos;
+            const std::vector<int32_t>& l = lists[w];  // sorted by cost, descending
+            for (size_t lo = 0, hi = l.size(), k = 0; lo < hi; ++k) {
+                const int32_t c = (k & 1) ? l[--hi] : l[lo++];
+                dir[pos * 4 + 0] = kstep_off[c];
+                dir[pos * 4 + 1] = plan.chunk_dir[(size_t)c * 4 + 1];
+                dir[pos * 4 + 2] = plan.chunk_dir[(size_t)c * 4 + 2];
+                dir[pos * 4 + 3] = plan.chunk_dir[(size_t)c * 4 + 3];
+                std::copy_n(&plan.chunk_meta[(size_t)c * kMetaInts], kMetaInts, &meta[pos * kMetaInts]);
+                ++pos;
+            }
+        }
+        for (int w = nw; w <= kMaxWarps; ++w) dev.warp_off[w] = (int32_t)pos;
+    }
     std::vector<int32_t> pairs(plan.tab_parent.size() * 2);
     for (size_t i = 0; i < plan.tab_parent.size(); ++i) pairs[2 * i] = plan.tab_parent[i], pairs[2 * i + 1] = plan.tab_hot[i];
     if ((rc = upload(plan.eta, &dev.eta, dev.bytes))) return rc;
     if ((rc = upload(pairs, &dev.tab_pairs, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
-    if ((rc = upload(plan.chunk_meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
+    if ((rc = upload(meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
     if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
     return SMX_OK;
@@ -115,6 +147,8 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.d_out = d.d_out;
     a.num_tiles = (N + kTile - 1) / kTile;
     a.n_hot = d.n_hot;
+    a.n_hot_rows = d.n_hot_rows;
+    for (int w = 0; w <= kMaxWarps; ++w) a.warp_off[w] = d.warp_off[w];
     a.n_tab = d.n_tab;
     a.n_chunks = d.n_chunks;
     a.n_levels = d.n_levels;

@@ -10,6 +10,7 @@ constexpr int kTile = 32;  // points per tile
 static_assert(kBlockWidth == 16, "lane mapping assumes 16 entries per block");
 static_assert(kChunkRows == 16, "the metadata record holds 16 row indices");
 constexpr int kKStepDoubles = 4 * kBlockWidth;  // one DMMA k-step (4 rows x 16 entries) of packed coefficients
+constexpr int kMaxWarps = 16;
 
 struct FastArgs {
     const double* eta;
@@ -20,8 +21,9 @@ struct FastArgs {
     const double* coef;      // packed in DMMA B-fragment order, see pack_coefficients()
     const double* c0;
     long long N, ldx, d_out, num_tiles;
-    int n_hot, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
+    int n_hot, n_hot_rows, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
     int level_off[kMaxLevels + 2];
+    int warp_off[kMaxWarps + 1];  // work items of warp w are [warp_off[w], warp_off[w + 1]) of the (re-ordered) directory
 };
 
 // One work item as the kernel sees it in shared memory: metadata record (smx_plan.h, kMetaInts) + packed coefficients.
@@ -29,7 +31,7 @@ struct alignas(16) ItemBuffer {
     int tab[16];      // value-table row of each entry (hot blocks)
     int deg[16];      // degree of each entry (0: dummy)
     int etaoff[16];   // offset of the entry's centres in `eta`
-    int ridx[16];     // value-table row of each coefficient row (0 beyond the item's rows)
+    int ridx[16];     // value-table rows, transposed: ridx[4 * k + s] = row 4 * s + k (0 beyond the item's rows)
     double eta0[16];  // first centre of each entry
     double coef[kChunkRows * kBlockWidth];
 };

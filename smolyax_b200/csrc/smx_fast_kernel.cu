@@ -37,10 +37,15 @@ namespace {
 constexpr int kXTileBytes = kTile * kBlockWidth * 8;  // 4096
 constexpr int kHotRegs = 8;                           // hot coordinates per lane kept in registers for the next tile
 
-struct alignas(1024) Stage {
-    double xs[kTile * kBlockWidth];  // TMA destination, 128-byte swizzle => 1024-byte alignment
+// Per-warp staging: the x tile (TMA destination, 128-byte swizzle => 1024-byte alignment; consumed into registers at
+// the start of the item, so one buffer is enough), two item buffers, and one mbarrier per item buffer (the x tile
+// travels with its item).
+struct alignas(1024) XTile {
+    double v[kTile * kBlockWidth];
+};
+struct alignas(16) ItemStage {
     ItemBuffer item[2];
-    unsigned long long bar[2];       // mbarriers: item buffer b (and the x tile that travels with that item)
+    unsigned long long bar[2];
 };
 
 // tile point t = gid + 8 * i  ->  position inside a value-table row: points (gid, gid + 8) and (gid + 16, gid + 24)
@@ -87,15 +92,15 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 }
 
 // One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
-__device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, Stage& st, int buf, int c, const int4 dir,
-                                           long long o, long long p0) {
+__device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, int c,
+                                           const int4 dir, long long o, long long p0) {
     const int ksteps = (dir.y + 3) >> 2;
     const unsigned coef_bytes = (unsigned)ksteps * kKStepDoubles * 8;
     const bool cold = !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
     bulk_copy(&st.item[buf], a.chunk_meta + (size_t)c * kMetaInts, kMetaInts * 4, &st.bar[buf]);
     bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);
-    if (cold) tma_load_2d(st.xs, xmap, dir.w, (int)p0, &st.bar[buf]);
+    if (cold) tma_load_2d(xs, xmap, dir.w, (int)p0, &st.bar[buf]);
 }
 
 template <int NW, int CTAS>
@@ -105,7 +110,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned carve-up (the launch adds 1 KiB of slack)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    Stage* stages = reinterpret_cast<Stage*>(base);                              // [NW]
+    XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
+    ItemStage* stages = reinterpret_cast<ItemStage*>(xtiles + NW);                // [NW]
     double* tab = reinterpret_cast<double*>(stages + NW);                         // [n_tab][kTabPitch] value table
     double* ypart = tab + (size_t)a.n_tab * kTabPitch;                            // [NW][32]
     int4* s_dir = reinterpret_cast<int4*>(ypart + NW * kTile);                    // [n_chunks]
@@ -115,7 +121,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tig = lane & 3, gid = lane >> 2;
-    Stage& st = stages[warp];
+    ItemStage& st = stages[warp];
+    double* xs = xtiles[warp].v;
 
     // ---- once per CTA: small tables to shared memory, mbarriers --------------------------------------------------------
     for (int i = tid; i < a.n_chunks; i += kThreads) s_dir[i] = __ldg(a.chunk_dir + i);
@@ -151,7 +158,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 double v = 1.0;
                 for (int k = s_hot_off[d]; k < s_hot_off[d + 1]; ++k) {
                     v *= (xv - s_eta[k]);
-                    tab[(1 + k) * kTabPitch + slot] = v;
+                    tab[(1 + hot_row(k)) * kTabPitch + slot] = v;
                 }
             };
 #pragma unroll
@@ -167,7 +174,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             const int t_begin = a.level_off[l], count = (a.level_off[l + 1] - t_begin) * kTile;
             for (int idx = tid; idx < count; idx += kThreads) {
                 const int ti = t_begin + (idx >> 5), s = idx & 31;
-                const int2 pr = s_pairs[ti - 1 - a.n_hot];
+                const int2 pr = s_pairs[ti - 1 - a.n_hot_rows];
                 tab[ti * kTabPitch + s] = tab[pr.x * kTabPitch + s] * tab[pr.y * kTabPitch + s];
             }
             __syncthreads();
@@ -177,12 +184,23 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         // ---- main: block-sparse contraction, one output at a time -------------------------------------------------------
         for (long long o = 0; o < a.d_out; ++o) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
-            if (warp < a.n_chunks && lane == 0) stage_item(a, &xmap, st, k_item & 1, warp, s_dir[warp], o, p0);
-            for (int c = warp; c < a.n_chunks; c += NW, ++k_item) {
+            const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
+            if (c_begin < c_end && lane == 0) stage_item(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], o, p0);
+            for (int c = c_begin; c < c_end; ++c, ++k_item) {
                 const int buf = k_item & 1;
                 const int4 dir = s_dir[c];
                 const ItemBuffer& ib = st.item[buf];
+                const int ksteps = (dir.y + 3) >> 2;
                 mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
+
+                // fragment loads of the first two k-steps go out first: their latency overlaps the basis-value work below
+                const int4 r4 = *reinterpret_cast<const int4*>(ib.ridx + 4 * tig);  // this lane's row of every k-step
+                const double2 b0 = *reinterpret_cast<const double2*>(ib.coef + 2 * lane);
+                const double2 b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                const double* ap0 = tab + r4.x * kTabPitch + 2 * gid;
+                const double* ap1 = tab + r4.y * kTabPitch + 2 * gid;
+                const double2 a0lo = *reinterpret_cast<const double2*>(ap0), a0hi = *reinterpret_cast<const double2*>(ap0 + 16);
+                const double2 a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
 
                 // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
                 double v[4][4];
@@ -202,33 +220,52 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const double* xr = st.xs + (gid + 8 * i) * kBlockWidth;
+                        const double* xr = xs + (gid + 8 * i) * kBlockWidth;
                         const double2 lo = *reinterpret_cast<const double2*>(xr + (((2 * tig) ^ gid) << 1));
                         const double2 hi = *reinterpret_cast<const double2*>(xr + (((2 * tig + 1) ^ gid) << 1));
                         v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                if (c + NW < a.n_chunks && lane == 0) stage_item(a, &xmap, st, buf ^ 1, c + NW, s_dir[c + NW], o, p0);
+                if (c + 1 < c_end && lane == 0) stage_item(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], o, p0);
 
-                // acc[i][j] (8 x 8 tiles) += A (value-table rows of this k-step) * B (packed coefficients)
+                // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients)
                 double acc[4][2][2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-                const int ksteps = (dir.y + 3) >> 2;
-#pragma unroll 2
-                for (int s = 0; s < ksteps; ++s) {
-                    const double* ap = tab + ib.ridx[4 * s + tig] * kTabPitch + 2 * gid;
-                    const double2 a01 = *reinterpret_cast<const double2*>(ap);
-                    const double2 a23 = *reinterpret_cast<const double2*>(ap + 16);
-                    const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
-                    const double af[4] = {a01.x, a01.y, a23.x, a23.y};
+                {
+                    const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        dmma(acc[i][0], af[i], b.x);
-                        dmma(acc[i][1], af[i], b.y);
+                        dmma(acc[i][0], af[i], b0.x);
+                        dmma(acc[i][1], af[i], b0.y);
+                    }
+                }
+                if (ksteps > 1) {
+                    const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dmma(acc[i][0], af[i], b1.x);
+                        dmma(acc[i][1], af[i], b1.y);
+                    }
+                }
+                if (ksteps > 2) {
+                    const int rws[2] = {r4.z, r4.w};
+#pragma unroll
+                    for (int s = 2; s < 4; ++s) {
+                        if (s >= ksteps) break;
+                        const double* ap = tab + rws[s - 2] * kTabPitch + 2 * gid;
+                        const double2 a01 = *reinterpret_cast<const double2*>(ap);
+                        const double2 a23 = *reinterpret_cast<const double2*>(ap + 16);
+                        const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
+                        const double af[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            dmma(acc[i][0], af[i], b.x);
+                            dmma(acc[i][1], af[i], b.y);
+                        }
                     }
                 }
 #pragma unroll
@@ -262,7 +299,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 }
 
 size_t smem_bytes(const FastDevice& d, int nw) {
-    return 1024 + (size_t)nw * sizeof(Stage) + ((size_t)d.n_tab * kTabPitch + (size_t)nw * kTile + (size_t)d.n_hot) * sizeof(double) +
+    return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + ((size_t)d.n_tab * kTabPitch + (size_t)nw * kTile + (size_t)d.n_hot) * sizeof(double) +
            (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1) * sizeof(int) + 16;
 }
 
@@ -307,8 +344,10 @@ int fast_kernel_prepare(FastDevice& d) {
     const bool fits4 = 2 * (smem_bytes(d, 4) + 1024) <= (size_t)smem_sm;
     const bool fits8 = smem_bytes(d, 8) <= (size_t)smem_optin;
     const bool fits12 = smem_bytes(d, 12) <= (size_t)smem_optin;
+    const bool fits16 = smem_bytes(d, 16) <= (size_t)smem_optin;
     d.warps = 0;
-    if (want == 12 && fits12) d.warps = 12;
+    if (want == 16 && fits16) d.warps = 16;
+    else if (want == 12 && fits12) d.warps = 12;
     else if (want == 8 && fits8) d.warps = 8;
     else if (want == 4 && fits4) d.warps = 4;
     else if (fits12) d.warps = 12;
@@ -321,6 +360,8 @@ int fast_kernel_prepare(FastDevice& d) {
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 8)));
     if (d.warps == 12)
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 12)));
+    if (d.warps == 16)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
     return SMX_OK;
 }
 
@@ -337,6 +378,7 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
     if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
     if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
+    if (d.warps == 16) return launch<16, 1>(map, a, d, x, y, st);
     return launch<12, 1>(map, a, d, x, y, st);
 }
 

@@ -345,7 +345,8 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         if (maxdeg[d] == 0) continue;
         ent_index[d] = (int32_t)plan.ent_dim.size();
         for (int a = 1; a <= maxdeg[d]; ++a) {
-            push_entry((int32_t)d, a, ++plan.n_hot);
+            push_entry((int32_t)d, a, 1 + hot_row(plan.n_hot));
+            ++plan.n_hot;
             ++plan.n_entries;
         }
     }
@@ -376,7 +377,8 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     for (int32_t r = 0; r < R; ++r) maxlevel = std::max(maxlevel, (int)row_key[r].size());
     plan.n_levels = maxlevel + 1;
     plan.level_off.assign((size_t)plan.n_levels + 2, 0);
-    int32_t next = 1 + plan.n_hot;
+    plan.n_hot_rows = (plan.n_hot + kBlockWidth - 1) / kBlockWidth * kBlockWidth;
+    int32_t next = 1 + plan.n_hot_rows;
     for (int32_t r = 0; r < R; ++r)
         if (row_key[r].size() == 1) row_tab[r] = hot_tab.at(row_key[r][0]);
     for (int l = 2; l <= maxlevel; ++l) {
@@ -475,7 +477,7 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     {
         std::vector<Chunk> mixed;
         size_t lo = 0, hi = chunks.size();
-        const size_t group = 8;
+        const size_t group = 12;  // = warps of the default CTA shape: every warp alternates big and small items
         bool front = true;
         while (lo < hi) {
             for (size_t g2 = 0; g2 < group && lo < hi; ++g2) mixed.push_back(std::move(front ? chunks[lo++] : chunks[--hi]));
@@ -507,7 +509,8 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             meta[i] = plan.ent_tab[e0 + i];
             meta[16 + i] = plan.ent_deg[e0 + i];
             meta[32 + i] = plan.ent_eta[e0 + i];
-            meta[48 + i] = i < rows ? plan.chunk_rows[r0 + i] : 0;
+            // row indices transposed for the kernel: position 4 * k + s holds row 4 * s + k (k-step s, A-fragment column k)
+            meta[48 + 4 * (i & 3) + (i >> 2)] = i < rows ? plan.chunk_rows[r0 + i] : 0;
             eta0[i] = plan.ent_eta0[e0 + i];
         }
         std::memcpy(meta + 64, eta0, sizeof(eta0));
@@ -520,7 +523,7 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
 
 void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y) {
     const int64_t d_out = plan.d_out;
-    std::vector<double> tab((size_t)plan.n_tab);
+    std::vector<double> tab((size_t)plan.n_tab, 1.0);
     std::vector<double> acc((size_t)d_out);
     auto pi = [&](const double* xp, int32_t e) {
         double v = 1.0;
@@ -532,8 +535,8 @@ void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ld
         tab[0] = 1.0;
         for (size_t e = 0; e < plan.ent_dim.size(); ++e)
             if (plan.ent_tab[e] > 0) tab[plan.ent_tab[e]] = pi(xp, (int32_t)e);
-        for (int32_t t = 1 + plan.n_hot; t < plan.n_tab; ++t)
-            tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot]] * tab[plan.tab_hot[t - 1 - plan.n_hot]];
+        for (int32_t t = 1 + plan.n_hot_rows; t < plan.n_tab; ++t)
+            tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot_rows]] * tab[plan.tab_hot[t - 1 - plan.n_hot_rows]];
         double* yp = y + p * d_out;
         for (int64_t o = 0; o < d_out; ++o) yp[o] = plan.c0[o];
         for (int32_t c = 0; c < plan.n_chunks; ++c) {

@@ -66,6 +66,7 @@ struct FastPlan {
     // cold blocks are padded so that they start at an even column of x.  Dummies have zero coefficients.
     int32_t n_entries = 0;               // real entries
     int32_t n_hot = 0;                   // hot prefix (real entries)
+    int32_t n_hot_rows = 0;              // value-table rows reserved for the hot entries (n_hot rounded up to a block)
     int32_t hot_dims = 0;                // the hot entries live on columns [0, hot_dims) of x
     std::vector<int32_t> ent_dim;        // column of x (dummies: a valid column)
     std::vector<int32_t> ent_deg;        // a >= 1, 0 for dummies (pi = 1)
@@ -74,8 +75,10 @@ struct FastPlan {
     std::vector<double> ent_eta0;        // first centre (pi_{j,1}(x) = x - eta0)
     std::vector<double> eta;             // centres, concatenated per dimension
 
-    // Value table, one row of 32 points per index:  [0] = 1,  [1 .. n_hot] = pi of hot entry (index-1),
-    // [n_hot+1 ..) = products of >= 2 hot pairs ("rows" of level >= 2), each parent * hot:
+    // Value table, one row of 32 points per index:  [0] = 1,  [1 + hot_row(h)] = pi of hot entry h, where hot_row()
+    // transposes every aligned block of 16 entries as a 4 x 4 matrix (so that the four lanes that read "their e-th
+    // entry" of a hot block touch four consecutive rows, i.e. four different bank groups),
+    // [1 + n_hot_rows ..) = products of >= 2 hot pairs ("rows" of level >= 2), each parent * hot:
     int32_t n_tab = 1;
     int32_t n_levels = 1;                // highest number of pairs in a hot part, plus one
     std::vector<int32_t> tab_parent;     // for index >= n_hot+1 (level >= 2): table indices of the two factors
@@ -97,6 +100,12 @@ struct FastPlan {
     int64_t padded_fma = 0;              // row slots * kBlockWidth
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
 };
+
+// value-table row (minus one) of hot entry h
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int32_t hot_row(int32_t h) { return (h & ~15) | ((h & 3) << 2) | ((h >> 2) & 3); }
 
 // Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
