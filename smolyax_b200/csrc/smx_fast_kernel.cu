@@ -4,7 +4,7 @@
 //
 //   I(x_p) = c_0 + sum_{e=(j,a)} pi_e(x_pj) * sum_r C[r][e] * m_r(x_p)
 //
-// One CTA works on one tile of 32 evaluation points at a time (12 or 8 warps and one CTA per SM, or 4 warps and two).
+// One CTA works on one tile of 32 evaluation points at a time (16, 12 or 8 warps and one CTA per SM, or 4 warps and two).
 //   * prologue : the CTA fills the value table in shared memory (one row of 32 points per index, pitch kTabPitch):
 //                row 0 = 1, then the 1-D basis values pi_e(x_p) of the hot entries (lane = point, running product over
 //                the Newton centres; the hot coordinates of the NEXT tile are already in registers, loaded during the
@@ -293,7 +293,9 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int w = 0; w < NW; ++w) s += ypart[w * kTile + tid];
                 y[(p0 + tid) * a.d_out + o] = s;
             }
-            __syncthreads();
+            // ypart is rewritten only after the barriers of the next prologue, the value table only by that prologue
+            // (every warp is past the barrier above): the last output of a tile needs no second barrier
+            if (o + 1 < a.d_out) __syncthreads();
         }
     }
 }
@@ -350,6 +352,7 @@ int fast_kernel_prepare(FastDevice& d) {
     else if (want == 12 && fits12) d.warps = 12;
     else if (want == 8 && fits8) d.warps = 8;
     else if (want == 4 && fits4) d.warps = 4;
+    else if (fits16) d.warps = 16;
     else if (fits12) d.warps = 12;
     else if (fits8) d.warps = 8;
     else if (fits4) d.warps = 4;
