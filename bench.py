@@ -84,7 +84,7 @@ def cpu_reference(wl, layout, seconds: float, repeats: int):
     bounded sample of the workload.  Returns (points*d_out/s, cores, sample description, per-repeat seconds)."""
     from oracle import oracle
 
-    cores = oracle.max_threads()
+    cores = oracle.use_all_cores()
     x = wl.points(max(cores * 4, 32), seed=123)
     t0 = time.perf_counter()
     oracle.evaluate(layout, x)

@@ -66,6 +66,15 @@ def max_threads() -> int:
     return int(lib().smo_max_threads())
 
 
+def use_all_cores() -> int:
+    """Let OpenMP use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().smo_set_num_threads(ctypes.c_int(n))
+    return max_threads()
+
+
 def compute_weights(nodes):
     nodes_, pn = _d(nodes)
     w = np.empty_like(nodes_)
