@@ -75,6 +75,7 @@ struct FastDevice {
     double* eta = nullptr;
     int32_t* tab_pairs = nullptr;
     int32_t* hot_off = nullptr;
+    int32_t* hot_pos = nullptr;
     int32_t* chunk_dir = nullptr;
     int32_t* chunk_meta = nullptr;
     double* coef = nullptr;

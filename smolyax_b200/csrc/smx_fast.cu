@@ -107,6 +107,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(plan.eta, &dev.eta, dev.bytes))) return rc;
     if ((rc = upload(pairs, &dev.tab_pairs, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
+    if ((rc = upload(plan.hot_pos, &dev.hot_pos, dev.bytes))) return rc;
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
     if ((rc = upload(meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
     if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
@@ -115,7 +116,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
 }
 
 void fast_free(FastDevice& d) {
-    void* ptrs[] = {d.eta, d.tab_pairs, d.hot_off, d.chunk_dir, d.chunk_meta, d.coef, d.c0};
+    void* ptrs[] = {d.eta, d.tab_pairs, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -138,6 +139,7 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
     a.hot_off = d.hot_off;
+    a.hot_pos = d.hot_pos;
     a.chunk_dir = reinterpret_cast<const int4*>(d.chunk_dir);
     a.chunk_meta = d.chunk_meta;
     a.coef = d.coef;

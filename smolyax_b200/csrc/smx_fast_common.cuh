@@ -16,6 +16,7 @@ struct FastArgs {
     const double* eta;
     const int2* tab_pairs;   // value-table rows of level >= 2: (parent row, hot row)
     const int32_t* hot_off;
+    const int32_t* hot_pos;  // entry index of hot pair k (dimension-major numbering, = index of its centre in eta)
     const int4* chunk_dir;   // per work item: first k-step of its packed coefficients, rows, flags, first column of x
     const int32_t* chunk_meta;
     const double* coef;      // packed in DMMA B-fragment order, see pack_coefficients()

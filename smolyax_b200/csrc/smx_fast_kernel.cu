@@ -118,6 +118,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);                // [n_hot] centres of the hot dimensions
     int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // [n_pairs]
     int* s_hot_off = reinterpret_cast<int*>(s_pairs + a.n_pairs);                 // [hot_dims + 1]
+    int* s_hot_row = s_hot_off + a.hot_dims + 1;                                  // [n_hot] value-table row of hot pair k
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tig = lane & 3, gid = lane >> 2;
@@ -129,6 +130,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     for (int i = tid; i < a.n_hot; i += kThreads) s_eta[i] = __ldg(a.eta + i);
     for (int i = tid; i < a.n_pairs; i += kThreads) s_pairs[i] = __ldg(a.tab_pairs + i);
     for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
+    for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
     if (lane == 0) {
         mbar_init(&st.bar[0], 1);
         mbar_init(&st.bar[1], 1);
@@ -158,7 +160,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 double v = 1.0;
                 for (int k = s_hot_off[d]; k < s_hot_off[d + 1]; ++k) {
                     v *= (xv - s_eta[k]);
-                    tab[(1 + hot_row(k)) * kTabPitch + slot] = v;
+                    tab[s_hot_row[k] * kTabPitch + slot] = v;
                 }
             };
 #pragma unroll
@@ -235,20 +237,27 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                const int km = dir.z >> 8;  // bit 2 s + j: k-step s touches entries of n-tile j at all
                 {
                     const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
+                    if (km & 1) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        dmma(acc[i][0], af[i], b0.x);
-                        dmma(acc[i][1], af[i], b0.y);
+                        for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b0.x);
+                    }
+                    if (km & 2) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b0.y);
                     }
                 }
                 if (ksteps > 1) {
                     const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
+                    if (km & 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        dmma(acc[i][0], af[i], b1.x);
-                        dmma(acc[i][1], af[i], b1.y);
+                        for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b1.x);
+                    }
+                    if (km & 8) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b1.y);
                     }
                 }
                 if (ksteps > 2) {
@@ -261,10 +270,13 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         const double2 a23 = *reinterpret_cast<const double2*>(ap + 16);
                         const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
                         const double af[4] = {a01.x, a01.y, a23.x, a23.y};
+                        if (km & (1 << (2 * s))) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            dmma(acc[i][0], af[i], b.x);
-                            dmma(acc[i][1], af[i], b.y);
+                            for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b.x);
+                        }
+                        if (km & (2 << (2 * s))) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b.y);
                         }
                     }
                 }
@@ -302,7 +314,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
 size_t smem_bytes(const FastDevice& d, int nw) {
     return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + ((size_t)d.n_tab * kTabPitch + (size_t)nw * kTile + (size_t)d.n_hot) * sizeof(double) +
-           (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1) * sizeof(int) + 16;
+           (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1 + d.n_hot) * sizeof(int) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

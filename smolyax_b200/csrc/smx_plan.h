@@ -75,7 +75,7 @@ struct FastPlan {
     std::vector<double> ent_eta0;        // first centre (pi_{j,1}(x) = x - eta0)
     std::vector<double> eta;             // centres, concatenated per dimension
 
-    // Value table, one row of 32 points per index:  [0] = 1,  [1 + hot_row(h)] = pi of hot entry h, where hot_row()
+    // Value table, one row of 32 points per index:  [0] = 1,  [1 + hot_row(e)] = pi of hot entry e, where hot_row()
     // transposes every aligned block of 16 entries as a 4 x 4 matrix (so that the four lanes that read "their e-th
     // entry" of a hot block touch four consecutive rows, i.e. four different bank groups),
     // [1 + n_hot_rows ..) = products of >= 2 hot pairs ("rows" of level >= 2), each parent * hot:
@@ -93,11 +93,14 @@ struct FastPlan {
     std::vector<int32_t> chunk_rows;     // value-table index of every row slot
     std::vector<double> coef;
     // the same information packed for the kernel: one directory entry and one metadata record per work item
-    std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags, first column of x
+    std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags | kmask << 8, first column of x
+    std::vector<int32_t> chunk_kmask;    // bit 2 s + j set: k-step s has a non-zero coefficient in entries 8 j .. 8 j + 7
     std::vector<int32_t> chunk_meta;     // kMetaInts ints per item: tab[16], deg[16], eta offset[16], row index[16], eta0[16] (doubles)
     std::vector<int32_t> hot_off;        // prefix sums of the degrees of the hot dimensions, size hot_dims + 1
+    std::vector<int32_t> hot_pos;        // entry index of hot pair (d, a), indexed hot_off[d] + a - 1 (hot entries are
+                                         // stored degree-major: blocks of equal degree share most of their rows)
     std::vector<double> c0;              // (d_out) constant term, includes the offset
-    int64_t padded_fma = 0;              // row slots * kBlockWidth
+    int64_t padded_fma = 0;              // FMAs per point and output the kernel executes: 32 per non-empty (k-step, half block)
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
 };
 
