@@ -74,6 +74,8 @@ struct FastDevice {
     int32_t level_off[kMaxLevels + 2] = {0};
     double* eta = nullptr;
     int32_t* tab_pairs = nullptr;
+    int32_t* tab_factors = nullptr;
+    int32_t n_flat = 0;
     int32_t* hot_off = nullptr;
     int32_t* hot_pos = nullptr;
     int32_t* chunk_dir = nullptr;

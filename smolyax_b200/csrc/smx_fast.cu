@@ -1,5 +1,7 @@
 // Fast evaluation path, host side: device upload of the plan (smx_plan.h), coefficient packing, launch.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "smx_fast_common.cuh"
 
@@ -55,6 +57,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     dev.n_chunks = plan.n_chunks;
     dev.hot_dims = plan.hot_dims;
     dev.n_pairs = (int32_t)plan.tab_parent.size();
+    dev.n_flat = (int32_t)(plan.tab_factors.size() / 4);
     if (plan.n_levels > kMaxLevels) return fail(SMX_ERR_UNSUPPORTED, "too many active dimensions per term");
     for (size_t l = 0; l < plan.level_off.size() && l < (size_t)kMaxLevels + 2; ++l) dev.level_off[l] = plan.level_off[l];
     for (int32_t c = 0; c < plan.n_chunks; ++c)
@@ -75,7 +78,11 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     std::vector<int32_t> dir((size_t)plan.n_chunks * 4), meta((size_t)plan.n_chunks * kMetaInts);
     {
         const int nw = dev.warps;
-        auto cost = [&](int32_t c) { return 2.0 + (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4); };
+        double ca = 2.0, cb = 1.0, cc = 0.0;  // cost model of an item: fixed + per k-step + extra for streaming x
+        if (const char* env = std::getenv("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf", &ca, &cb, &cc);
+        auto cost = [&](int32_t c) {
+            return ca + cb * (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4) + ((plan.chunk_flags[c] & kChunkHot) ? 0.0 : cc);
+        };
         std::vector<int32_t> by_cost((size_t)plan.n_chunks);
         for (int32_t c = 0; c < plan.n_chunks; ++c) by_cost[c] = c;
         std::stable_sort(by_cost.begin(), by_cost.end(), [&](int32_t x1, int32_t x2) { return cost(x1) > cost(x2); });
@@ -106,6 +113,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     for (size_t i = 0; i < plan.tab_parent.size(); ++i) pairs[2 * i] = plan.tab_parent[i], pairs[2 * i + 1] = plan.tab_hot[i];
     if ((rc = upload(plan.eta, &dev.eta, dev.bytes))) return rc;
     if ((rc = upload(pairs, &dev.tab_pairs, dev.bytes, 2))) return rc;
+    if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
     if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
     if ((rc = upload(plan.hot_pos, &dev.hot_pos, dev.bytes))) return rc;
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
@@ -116,7 +124,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
 }
 
 void fast_free(FastDevice& d) {
-    void* ptrs[] = {d.eta, d.tab_pairs, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0};
+    void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -138,6 +146,8 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     FastArgs a;
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
+    a.tab_factors = reinterpret_cast<const int4*>(d.tab_factors);
+    a.n_flat = d.n_flat;
     a.hot_off = d.hot_off;
     a.hot_pos = d.hot_pos;
     a.chunk_dir = reinterpret_cast<const int4*>(d.chunk_dir);

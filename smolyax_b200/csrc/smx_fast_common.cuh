@@ -15,6 +15,8 @@ constexpr int kMaxWarps = 16;
 struct FastArgs {
     const double* eta;
     const int2* tab_pairs;   // value-table rows of level >= 2: (parent row, hot row)
+    const int4* tab_factors; // rows of level 2..4 as products of up to four hot rows
+    int n_flat;              // number of those rows (they come first among the product rows)
     const int32_t* hot_off;
     const int32_t* hot_pos;  // entry index of hot pair k (dimension-major numbering, = index of its centre in eta)
     const int4* chunk_dir;   // per work item: first k-step of its packed coefficients, rows, flags, first column of x

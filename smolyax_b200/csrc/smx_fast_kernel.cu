@@ -87,23 +87,31 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                  : "memory");
 }
 // D (8x8, fp64) += A (8x4, row) * B (4x8, col): one value of A and B per lane, two of D
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+template <int ABL = 0>
+__device__ __forceinline__ void dmma_(double (&c)[2], double a, double b) {
+    if (ABL == 1) {  // keep the data dependence, stay off the FP64 pipe
+        c[0] = __longlong_as_double(__double_as_longlong(c[0]) ^ __double_as_longlong(a));
+        c[1] = __longlong_as_double(__double_as_longlong(c[1]) ^ __double_as_longlong(b));
+        return;
+    }
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
 // One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
+template <int ABL = 0>
 __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, int c,
                                            const int4 dir, long long o, long long p0) {
     const int ksteps = (dir.y + 3) >> 2;
     const unsigned coef_bytes = (unsigned)ksteps * kKStepDoubles * 8;
-    const bool cold = !(dir.z & kChunkHot);
+    const bool cold = ABL == 3 ? false : !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
     bulk_copy(&st.item[buf], a.chunk_meta + (size_t)c * kMetaInts, kMetaInts * 4, &st.bar[buf]);
     bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);
     if (cold) tma_load_2d(xs, xmap, dir.w, (int)p0, &st.bar[buf]);
 }
 
-template <int NW, int CTAS>
+// ABL != 0 are timing experiments (wrong results on purpose): 1 = no DMMA, 2 = no prologue, 3 = no x tiles / basis values
+template <int NW, int CTAS, int ABL = 0>
 __global__ void __launch_bounds__(NW * 32, CTAS)
 fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -113,9 +121,9 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
     ItemStage* stages = reinterpret_cast<ItemStage*>(xtiles + NW);                // [NW]
     double* tab = reinterpret_cast<double*>(stages + NW);                         // [n_tab][kTabPitch] value table
-    double* ypart = tab + (size_t)a.n_tab * kTabPitch;                            // [NW][32]
-    int4* s_dir = reinterpret_cast<int4*>(ypart + NW * kTile);                    // [n_chunks]
-    double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);                // [n_hot] centres of the hot dimensions
+    int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)a.n_tab * kTabPitch);     // [n_chunks] item directory
+    int4* s_fac = s_dir + a.n_chunks;                                             // [n_flat] hot rows of each product row
+    double* s_eta = reinterpret_cast<double*>(s_fac + a.n_flat);                  // [n_hot] centres of the hot dimensions
     int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // [n_pairs]
     int* s_hot_off = reinterpret_cast<int*>(s_pairs + a.n_pairs);                 // [hot_dims + 1]
     int* s_hot_row = s_hot_off + a.hot_dims + 1;                                  // [n_hot] value-table row of hot pair k
@@ -131,6 +139,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     for (int i = tid; i < a.n_pairs; i += kThreads) s_pairs[i] = __ldg(a.tab_pairs + i);
     for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
     for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
+    for (int i = tid; i < a.n_flat; i += kThreads) s_fac[i] = __ldg(a.tab_factors + i);
     if (lane == 0) {
         mbar_init(&st.bar[0], 1);
         mbar_init(&st.bar[1], 1);
@@ -154,7 +163,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
         // ---- prologue: value table = 1 | 1-D basis values of the hot entries | products of hot pairs, level by level ----
         if (tid < kTile) tab[tid] = 1.0;
-        {
+        if (ABL != 2) {
             const int slot = t_slot(lane);
             auto hot_dim = [&](int d, double xv) {
                 double v = 1.0;
@@ -172,14 +181,27 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             }
         }
         __syncthreads();
-        for (int l = 2; l < a.n_levels; ++l) {
-            const int t_begin = a.level_off[l], count = (a.level_off[l + 1] - t_begin) * kTile;
+        if (ABL != 2) {
+            // products of 2..4 hot pairs in one pass straight from the hot rows (row 0 = 1 pads short products) ..
+            const int flat_begin = 1 + a.n_hot_rows, count = a.n_flat * kTile;
+#pragma unroll 4
             for (int idx = tid; idx < count; idx += kThreads) {
-                const int ti = t_begin + (idx >> 5), s = idx & 31;
-                const int2 pr = s_pairs[ti - 1 - a.n_hot_rows];
-                tab[ti * kTabPitch + s] = tab[pr.x * kTabPitch + s] * tab[pr.y * kTabPitch + s];
+                const int k = idx >> 5, s = idx & 31;
+                const int4 f = s_fac[k];
+                tab[(flat_begin + k) * kTabPitch + s] = (tab[f.x * kTabPitch + s] * tab[f.y * kTabPitch + s]) *
+                                                        (tab[f.z * kTabPitch + s] * tab[f.w * kTabPitch + s]);
             }
             __syncthreads();
+            // .. and, only for hot parts of five and more pairs, level by level from their parents
+            for (int l = 5; l < a.n_levels; ++l) {
+                const int t_begin = a.level_off[l], cnt = (a.level_off[l + 1] - t_begin) * kTile;
+                for (int idx = tid; idx < cnt; idx += kThreads) {
+                    const int ti = t_begin + (idx >> 5), s = idx & 31;
+                    const int2 pr = s_pairs[ti - 1 - a.n_hot_rows];
+                    tab[ti * kTabPitch + s] = tab[pr.x * kTabPitch + s] * tab[pr.y * kTabPitch + s];
+                }
+                __syncthreads();
+            }
         }
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);  // lands during the main loop
 
@@ -187,7 +209,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         for (long long o = 0; o < a.d_out; ++o) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
-            if (c_begin < c_end && lane == 0) stage_item(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], o, p0);
+            if (c_begin < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], o, p0);
             for (int c = c_begin; c < c_end; ++c, ++k_item) {
                 const int buf = k_item & 1;
                 const int4 dir = s_dir[c];
@@ -206,7 +228,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
                 // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
                 double v[4][4];
-                if (dir.z & kChunkHot) {
+                if (ABL == 3 || (dir.z & kChunkHot)) {
                     const int4 t4 = *reinterpret_cast<const int4*>(ib.tab + 4 * tig);
                     const int tabs[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
@@ -229,7 +251,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                if (c + 1 < c_end && lane == 0) stage_item(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], o, p0);
+                if (c + 1 < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], o, p0);
 
                 // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients)
                 double acc[4][2][2];
@@ -242,22 +264,22 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
                     if (km & 1) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b0.x);
+                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b0.x);
                     }
                     if (km & 2) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b0.y);
+                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b0.y);
                     }
                 }
                 if (ksteps > 1) {
                     const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
                     if (km & 4) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b1.x);
+                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b1.x);
                     }
                     if (km & 8) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b1.y);
+                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b1.y);
                     }
                 }
                 if (ksteps > 2) {
@@ -272,11 +294,11 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         const double af[4] = {a01.x, a01.y, a23.x, a23.y};
                         if (km & (1 << (2 * s))) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dmma(acc[i][0], af[i], b.x);
+                            for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b.x);
                         }
                         if (km & (2 << (2 * s))) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dmma(acc[i][1], af[i], b.y);
+                            for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b.y);
                         }
                     }
                 }
@@ -296,24 +318,24 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             }
             if (tig == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ypart[warp * kTile + gid + 8 * i] = tot[i];
+                for (int i = 0; i < 4; ++i) xs[gid + 8 * i] = tot[i];  // the warp's x buffer is idle now: reuse it for its partial sums
             }
             __syncthreads();
             if (tid < kTile && p0 + tid < a.N) {
                 double s = __ldg(a.c0 + o);
 #pragma unroll
-                for (int w = 0; w < NW; ++w) s += ypart[w * kTile + tid];
+                for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
                 y[(p0 + tid) * a.d_out + o] = s;
             }
-            // ypart is rewritten only after the barriers of the next prologue, the value table only by that prologue
-            // (every warp is past the barrier above): the last output of a tile needs no second barrier
+            // the x buffers are rewritten (by TMA) only after the barriers of the next prologue, the value table only by that
+            // prologue (every warp is past the barrier above): the last output of a tile needs no second barrier
             if (o + 1 < a.d_out) __syncthreads();
         }
     }
 }
 
 size_t smem_bytes(const FastDevice& d, int nw) {
-    return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + ((size_t)d.n_tab * kTabPitch + (size_t)nw * kTile + (size_t)d.n_hot) * sizeof(double) +
+    return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + ((size_t)d.n_tab * kTabPitch + (size_t)d.n_hot) * sizeof(double) + (size_t)d.n_flat * sizeof(int4) + 16 +
            (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1 + d.n_hot) * sizeof(int) + 16;
 }
 
@@ -336,10 +358,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int NW, int CTAS>
+template <int NW, int CTAS, int ABL = 0>
 int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * CTAS);
-    fast_eval_kernel<NW, CTAS><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
+    if (ABL != 0)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW)));
+    fast_eval_kernel<NW, CTAS, ABL><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_eval_kernel");
     return SMX_OK;
 }
@@ -393,7 +417,13 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
     if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
     if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
-    if (d.warps == 16) return launch<16, 1>(map, a, d, x, y, st);
+    if (d.warps == 16) {
+        static const int ablate = std::getenv("SMX_FAST_ABLATE") ? std::atoi(std::getenv("SMX_FAST_ABLATE")) : 0;
+        if (ablate == 1) return launch<16, 1, 1>(map, a, d, x, y, st);  // timing experiments, results are wrong on purpose
+        if (ablate == 2) return launch<16, 1, 2>(map, a, d, x, y, st);
+        if (ablate == 3) return launch<16, 1, 3>(map, a, d, x, y, st);
+        return launch<16, 1>(map, a, d, x, y, st);
+    }
     return launch<12, 1>(map, a, d, x, y, st);
 }
 

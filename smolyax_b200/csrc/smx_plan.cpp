@@ -396,6 +396,9 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             row_tab[r] = next++;
             plan.tab_parent.push_back(row_tab[row_id.at(parent)]);
             plan.tab_hot.push_back(hot_tab.at(row_key[r].back()));
+            if (l <= 4) {  // rows of up to four pairs are also stored as a flat product of hot rows (one pass, no level order)
+                for (int f = 0; f < 4; ++f) plan.tab_factors.push_back(f < l ? hot_tab.at(row_key[r][f]) : 0);
+            }
         }
         plan.level_off[l + 1] = next;
     }

@@ -84,6 +84,7 @@ struct FastPlan {
     std::vector<int32_t> tab_parent;     // for index >= n_hot+1 (level >= 2): table indices of the two factors
     std::vector<int32_t> tab_hot;
     std::vector<int32_t> level_off;      // table indices of level l (l >= 2) are [level_off[l], level_off[l+1])
+    std::vector<int32_t> tab_factors;    // 4 ints per row of level 2..4: the hot rows whose product it is (0 = the ones row)
 
     // work items: (entry block, slice of its row list); coefficients [row slot][d_out][kBlockWidth]
     int32_t n_chunks = 0;
