@@ -55,6 +55,8 @@ typedef struct {
 /* Flags for smx_interp_desc.flags */
 #define SMX_KEEP_GROUPS 1u   /* also upload the reference layout (needed by gradient / integral / barycentric mode) */
 #define SMX_NO_FAST_PATH 2u  /* do not build the hierarchical fast path: smx_eval runs the per-summand kernels */
+#define SMX_GRAD_FINITE_AT_NODES 4u /* fast gradient: return the true (finite) derivative where a coordinate sits on a
+                                       node, instead of the NaN the reference produces there (barycentric.py:152-154) */
 
 typedef struct {
     int64_t d_in;
@@ -77,7 +79,8 @@ int smx_destroy(smx_interp* h);
  * x: (N, ldx) row-major device doubles, ldx >= d_in.  Results are written (not accumulated).
  * smx_eval      replaces SmolyakBarycentricInterpolator.__call__   interpolation.py:264-304 -> y (N, d_out)
  * smx_gradient  replaces SmolyakBarycentricInterpolator.gradient   interpolation.py:306-345 -> J (N, d_out, d_in)
- *               (NaN in J[p,:,dim] when x[p,dim] sits on a node of that dimension, as barycentric.py:152-154)
+ *               (NaN in J[p,:,dim] when x[p,dim] sits on a node of that dimension, as barycentric.py:152-154,
+ *               unless the handle was created with SMX_GRAD_FINITE_AT_NODES)
  * smx_integral  replaces SmolyakBarycentricInterpolator.integral   interpolation.py:347-390 -> q (d_out)        */
 int smx_eval(smx_interp* h, const double* x, int64_t N, int64_t ldx, double* y, void* stream);
 int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double* J, void* stream);

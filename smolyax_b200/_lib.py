@@ -14,6 +14,7 @@ from . import _build
 
 SMX_KEEP_GROUPS = 1
 SMX_NO_FAST_PATH = 2
+SMX_GRAD_FINITE_AT_NODES = 4
 
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "out of device memory", 4: "unsupported shape", 5: "no sm_100 device"}
 

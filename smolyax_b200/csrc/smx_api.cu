@@ -29,7 +29,7 @@ struct smx_interp {
     int device = 0;
     int64_t d_in = 0, d_out = 0;
     smx_info info{};
-    bool has_fast = false, has_groups = false;
+    bool has_fast = false, has_groups = false, grad_finite = false;
     FastDevice fast;
     std::vector<SeamGroup> groups;
     std::vector<void*> owned;  // device allocations behind `groups`
@@ -144,6 +144,7 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
         views.push_back(v);
     }
 
+    h->grad_finite = (desc->flags & SMX_GRAD_FINITE_AT_NODES) != 0;
     bool want_fast = !(desc->flags & SMX_NO_FAST_PATH);
     bool want_groups = (desc->flags & SMX_KEEP_GROUPS) != 0 || !want_fast;
     if (want_fast) {
@@ -236,9 +237,10 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
     if (!h || N < 0) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: bad arguments");
     if (N == 0) return SMX_OK;
     if (!x || !J || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: null buffer or ldx < d_in");
-    if (!h->has_groups && h->info.n_summands > 0)
-        return fail(SMX_ERR_INVALID_ARG, "smx_gradient: handle was created without SMX_KEEP_GROUPS");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->has_fast && h->fast.grad_ok) return fast_gradient(h->fast, x, N, ldx, J, !h->grad_finite, st);
+    if (!h->has_groups && h->info.n_summands > 0)
+        return fail(SMX_ERR_INVALID_ARG, "smx_gradient: no derivative sets and no reference layout (SMX_KEEP_GROUPS) on this handle");
     SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * h->d_out * h->d_in, st));
     int rc;
     for (const SeamGroup& g : h->groups)

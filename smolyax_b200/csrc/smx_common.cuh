@@ -82,6 +82,11 @@ struct FastDevice {
     int32_t* chunk_meta = nullptr;
     double* coef = nullptr;
     double* c0 = nullptr;
+    int32_t n_sets = 0, n_gd = 0;   // coefficient sets per row slot; hot dimensions with a derivative set
+    bool grad_ok = false;           // the plan carries derivative sets (or needs none): smx_gradient can use the fast path
+    int32_t* grad_dims = nullptr;
+    int32_t* nan_off = nullptr;     // per dimension: the nodes at which the reference returns NaN gradients
+    double* nan_nodes = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
@@ -89,5 +94,6 @@ struct FastDevice {
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);
 int fast_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
+int fast_gradient(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st);
 
 }  // namespace smx

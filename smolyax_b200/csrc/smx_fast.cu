@@ -22,7 +22,7 @@ int upload(const std::vector<T>& v, T** dptr, int64_t& bytes, size_t min_elems =
 // lane = 4 * gid + tig, n-tile j:   packed[s][lane][j] = C[row 4s + tig][entry 4 * (gid >> 1) + 2 * j + (gid & 1)]
 // (rows beyond the item's are zero).  One LDS.128 per lane and k-step, consecutive lanes at consecutive addresses.
 void pack_coefficients(const FastPlan& plan, std::vector<double>& packed, std::vector<int32_t>& kstep_off) {
-    const size_t dout = (size_t)plan.d_out;
+    const size_t dout = (size_t)plan.n_sets;  // every coefficient set (outputs, then derivative sets) is packed alike
     kstep_off.assign((size_t)plan.n_chunks + 1, 0);
     for (int32_t c = 0; c < plan.n_chunks; ++c) {
         const int32_t rows = plan.chunk_off[c + 1] - plan.chunk_off[c];
@@ -120,18 +120,40 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
     if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
+    dev.n_sets = plan.n_sets;
+    dev.n_gd = (int32_t)plan.grad_dims.size();
+    dev.grad_ok = plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) && (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0);
+    if ((rc = upload(plan.grad_dims, &dev.grad_dims, dev.bytes))) return rc;
+    if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
+    if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
     return SMX_OK;
 }
 
 void fast_free(FastDevice& d) {
-    void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0};
+    void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0,
+                    d.grad_dims, d.nan_off, d.nan_nodes};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
 }
 
-int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
-    if (N == 0) return SMX_OK;
+namespace {
+
+// J[p, :, dim] = NaN where x[p, dim] sits on an interpolation node of that dimension (reference barycentric.py:152-154)
+__global__ void nan_at_nodes_kernel(const double* __restrict__ x, long long N, long long ldx, long long d_in, long long d_out,
+                                    const int32_t* __restrict__ nan_off, const double* __restrict__ nan_nodes, double* __restrict__ J) {
+    const long long total = N * d_in;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / d_in, dim = i - p * d_in;
+        const double xv = x[p * ldx + dim];
+        bool hit = false;
+        for (int k = nan_off[dim]; k < nan_off[dim + 1]; ++k) hit |= (xv == nan_nodes[k]);
+        if (hit)
+            for (long long o = 0; o < d_out; ++o) J[(p * d_out + o) * d_in + dim] = nan("");
+    }
+}
+
+int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, int gradient, cudaStream_t st) {
     // TMA needs 16-byte aligned rows.  Anything else (odd pitch, odd base address) is first packed into an aligned
     // scratch copy on the same stream; callers that care about the last few percent pass aligned rows.
     double* scratch = nullptr;
@@ -158,6 +180,10 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.ldx = ldx;
     a.d_out = d.d_out;
     a.num_tiles = (N + kTile - 1) / kTile;
+    a.gradient = gradient;
+    a.n_gd = d.n_gd;
+    a.grad_dims = d.grad_dims;
+    a.d_in = d.d_in;
     a.n_hot = d.n_hot;
     a.n_hot_rows = d.n_hot_rows;
     for (int w = 0; w <= kMaxWarps; ++w) a.warp_off[w] = d.warp_off[w];
@@ -167,9 +193,32 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.hot_dims = d.hot_dims;
     a.n_pairs = d.n_pairs;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
-    const int rc = fast_kernel_launch(d, a, x, y, st);
+    const int rc = fast_kernel_launch(d, a, x, out, st);
     if (scratch) cudaFreeAsync(scratch, st);
     return rc;
+}
+
+}  // namespace
+
+int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
+    if (N == 0) return SMX_OK;
+    return run_fast(d, x, N, ldx, y, 0, st);
+}
+
+int fast_gradient(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st) {
+    if (N == 0) return SMX_OK;
+    if (!d.grad_ok) return fail(SMX_ERR_UNSUPPORTED, "plan has no derivative sets");
+    // dimensions without any entry keep derivative zero; everything else is written by the kernel
+    SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * d.d_out * d.d_in, st));
+    int rc = run_fast(d, x, N, ldx, J, 1, st);
+    if (rc) return rc;
+    if (nan_at_nodes) {
+        const long long total = (long long)N * d.d_in;
+        const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)d.sm_count * 16);
+        nan_at_nodes_kernel<<<blocks, 256, 0, st>>>(x, N, ldx, d.d_in, d.d_out, d.nan_off, d.nan_nodes, J);
+        SMX_LAUNCH_CHECK("nan_at_nodes_kernel");
+    }
+    return SMX_OK;
 }
 
 }  // namespace smx

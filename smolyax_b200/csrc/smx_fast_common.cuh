@@ -24,6 +24,12 @@ struct FastArgs {
     const double* coef;      // packed in DMMA B-fragment order, see pack_coefficients()
     const double* c0;
     long long N, ldx, d_out, num_tiles;
+    // gradient mode: y is J (N, d_out, d_in); pass q of output o is the function itself (q = 0: stores the row sums of the
+    // cold blocks, which are the derivatives w.r.t. their columns) or the derivative set of hot dimension grad_dims[q - 1]
+    int gradient;            // 0: values, 1: gradient
+    int n_gd;                // number of hot dimensions with a derivative set
+    const int32_t* grad_dims;
+    long long d_in;
     int n_hot, n_hot_rows, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
     int level_off[kMaxLevels + 2];
     int warp_off[kMaxWarps + 1];  // work items of warp w are [warp_off[w], warp_off[w + 1]) of the (re-ordered) directory

@@ -106,12 +106,12 @@ __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap*
     const bool cold = ABL == 3 ? false : !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
     bulk_copy(&st.item[buf], a.chunk_meta + (size_t)c * kMetaInts, kMetaInts * 4, &st.bar[buf]);
-    bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);
+    bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);  // o = set
     if (cold) tma_load_2d(xs, xmap, dir.w, (int)p0, &st.bar[buf]);
 }
 
 // ABL != 0 are timing experiments (wrong results on purpose): 1 = no DMMA, 2 = no prologue, 3 = no x tiles / basis values
-template <int NW, int CTAS, int ABL = 0>
+template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2>
 __global__ void __launch_bounds__(NW * 32, CTAS)
 fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -205,11 +205,21 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         }
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);  // lands during the main loop
 
-        // ---- main: block-sparse contraction, one output at a time -------------------------------------------------------
-        for (long long o = 0; o < a.d_out; ++o) {
+        // ---- main: block-sparse contraction, one coefficient set at a time ------------------------------------------------
+        // values: set = output.  gradient: per output, the function's own set (whose cold-block row sums are the
+        // derivatives w.r.t. the cold columns) followed by one derivative set per hot dimension.
+        const int n_pass = GRAD ? (int)a.d_out * (1 + a.n_gd) : (int)a.d_out;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            long long o = pass, set = pass;
+            int gq = 0;
+            if (GRAD) {
+                o = pass / (1 + a.n_gd);
+                gq = pass - (int)o * (1 + a.n_gd);
+                set = gq == 0 ? o : a.d_out + o * a.n_gd + (gq - 1);
+            }
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
-            if (c_begin < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], o, p0);
+            if (c_begin < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], set, p0);
             for (int c = c_begin; c < c_end; ++c, ++k_item) {
                 const int buf = k_item & 1;
                 const int4 dir = s_dir[c];
@@ -220,11 +230,12 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 // fragment loads of the first two k-steps go out first: their latency overlaps the basis-value work below
                 const int4 r4 = *reinterpret_cast<const int4*>(ib.ridx + 4 * tig);  // this lane's row of every k-step
                 const double2 b0 = *reinterpret_cast<const double2*>(ib.coef + 2 * lane);
-                const double2 b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                double2 b1 = make_double2(0.0, 0.0), a1lo = b1, a1hi = b1;
+                if (EARLY >= 2) b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
                 const double* ap0 = tab + r4.x * kTabPitch + 2 * gid;
                 const double* ap1 = tab + r4.y * kTabPitch + 2 * gid;
                 const double2 a0lo = *reinterpret_cast<const double2*>(ap0), a0hi = *reinterpret_cast<const double2*>(ap0 + 16);
-                const double2 a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
+                if (EARLY >= 2) a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
 
                 // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
                 double v[4][4];
@@ -251,7 +262,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                if (c + 1 < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], o, p0);
+                if (c + 1 < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], set, p0);
 
                 // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients)
                 double acc[4][2][2];
@@ -272,6 +283,10 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                 }
                 if (ksteps > 1) {
+                    if (EARLY < 2) {
+                        b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                        a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
+                    }
                     const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
                     if (km & 4) {
 #pragma unroll
@@ -302,6 +317,26 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         }
                     }
                 }
+                if (GRAD && gq == 0 && !(dir.z & kChunkHot)) {
+                    // d I_o / d x_j for the block's columns j: pi_e = x_j - eta_0, so the derivative is the row sum itself
+                    const int4 dg = *reinterpret_cast<const int4*>(ib.deg + 4 * tig);
+                    const bool split = dir.z & kChunkSplit;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long p = p0 + gid + 8 * i;
+                        if (p < a.N) {
+                            double* jr = y + (p * a.d_out + o) * a.d_in + dir.w + 4 * tig;
+                            const double g4[4] = {acc[i][0][0], acc[i][0][1], acc[i][1][0], acc[i][1][1]};
+                            const int d4[4] = {dg.x, dg.y, dg.z, dg.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (d4[e] == 0) continue;      // dummy entry: its column belongs to someone else
+                                if (split) atomicAdd(jr + e, g4[e]);  // at most a few items per block; J starts at zero
+                                else jr[e] = g4[e];
+                            }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     tot[i] = fma(v[i][0], acc[i][0][0], tot[i]);
@@ -321,15 +356,16 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int i = 0; i < 4; ++i) xs[gid + 8 * i] = tot[i];  // the warp's x buffer is idle now: reuse it for its partial sums
             }
             __syncthreads();
-            if (tid < kTile && p0 + tid < a.N) {
-                double s = __ldg(a.c0 + o);
+            if (tid < kTile && p0 + tid < a.N && !(GRAD && gq == 0)) {
+                double s = __ldg(a.c0 + set);
 #pragma unroll
                 for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
-                y[(p0 + tid) * a.d_out + o] = s;
+                if (GRAD) y[((p0 + tid) * a.d_out + o) * a.d_in + __ldg(a.grad_dims + gq - 1)] = s;
+                else y[(p0 + tid) * a.d_out + o] = s;
             }
             // the x buffers are rewritten (by TMA) only after the barriers of the next prologue, the value table only by that
             // prologue (every warp is past the barrier above): the last output of a tile needs no second barrier
-            if (o + 1 < a.d_out) __syncthreads();
+            if (pass + 1 < n_pass) __syncthreads();
         }
     }
 }
@@ -358,12 +394,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int NW, int CTAS, int ABL = 0>
+template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2>
 int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * CTAS);
-    if (ABL != 0)
-        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW)));
-    fast_eval_kernel<NW, CTAS, ABL><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
+    if (ABL != 0 || GRAD || EARLY != 2)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW)));
+    fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_eval_kernel");
     return SMX_OK;
 }
@@ -399,8 +435,10 @@ int fast_kernel_prepare(FastDevice& d) {
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 8)));
     if (d.warps == 12)
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 12)));
-    if (d.warps == 16)
+    if (d.warps == 16) {
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1, 0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
+    }
     return SMX_OK;
 }
 
@@ -415,6 +453,12 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
+    if (a.gradient) {
+        if (d.warps == 4) return launch<4, 2, 0, true>(map, a, d, x, y, st);
+        if (d.warps == 8) return launch<8, 1, 0, true>(map, a, d, x, y, st);
+        if (d.warps == 16) return launch<16, 1, 0, true>(map, a, d, x, y, st);
+        return launch<12, 1, 0, true>(map, a, d, x, y, st);
+    }
     if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
     if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
     if (d.warps == 16) {
@@ -422,7 +466,10 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
         if (ablate == 1) return launch<16, 1, 1>(map, a, d, x, y, st);  // timing experiments, results are wrong on purpose
         if (ablate == 2) return launch<16, 1, 2>(map, a, d, x, y, st);
         if (ablate == 3) return launch<16, 1, 3>(map, a, d, x, y, st);
-        return launch<16, 1>(map, a, d, x, y, st);
+        // 16 warps leave 128 registers per thread: pre-loading one k-step (not two) keeps the kernel spill free (measured)
+        static const int early = std::getenv("SMX_FAST_EARLY") ? std::atoi(std::getenv("SMX_FAST_EARLY")) : 1;
+        if (early == 2) return launch<16, 1>(map, a, d, x, y, st);
+        return launch<16, 1, 0, false, 1>(map, a, d, x, y, st);
     }
     return launch<12, 1>(map, a, d, x, y, st);
 }

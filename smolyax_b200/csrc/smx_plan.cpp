@@ -104,7 +104,7 @@ struct Summand {
 }  // namespace
 
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
-                            FastPlan& plan) {
+                            FastPlan& plan, bool with_gradient) {
     plan = FastPlan();
     plan.d_in = d_in;
     plan.d_out = d_out;
@@ -297,8 +297,6 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             for (auto& th : pool) th.join();
         }
     }
-    plan.c0.resize((size_t)d_out);
-    for (int64_t o = 0; o < d_out; ++o) plan.c0[o] = (double)C[o];
 
     // ---- 6. hot parts: every term minus its leading (largest-dimension) pair ---------------------------------
     std::unordered_map<Key, int32_t, KeyHash> row_id;  // hot part -> provisional row id (0 = empty product)
@@ -376,6 +374,65 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     std::unordered_map<int64_t, int32_t> hot_tab;
     for (size_t e = 0; e < plan.ent_dim.size(); ++e)
         if (plan.ent_tab[e] > 0) hot_tab[(int64_t)plan.ent_dim[e] * kCode + plan.ent_deg[e]] = plan.ent_tab[e];
+
+    // ---- 7b. gradient coefficient sets ---------------------------------------------------------------------------------
+    // d/dx_i of the interpolant is a polynomial over the same term set: a term with the pair (i, b) contributes to the
+    // terms with (i, k), k < b, through  pi_b' = sum_k D[b][k] pi_k  (D from pi_b = pi_{b-1} (x - eta_{b-1})).
+    // One set per output and hot dimension with an entry; cold dimensions need none (pi = x - eta_0, pi' = 1).
+    std::vector<std::vector<ld>> Cd;  // [grad dim][T * d_out]
+    if (with_gradient) {
+        for (int64_t d = 0; d <= hot_dim_max; ++d)
+            if (maxdeg[d] > 0) plan.grad_dims.push_back((int32_t)d);
+        const double bytes = (double)plan.grad_dims.size() * (double)T * (double)d_out * sizeof(ld);
+        if (bytes > 3.0e9) plan.grad_dims.clear();  // huge d_out: the gradient stays on the per-summand kernels
+        Cd.assign(plan.grad_dims.size(), std::vector<ld>());
+        for (size_t h = 0; h < plan.grad_dims.size(); ++h) {
+            const int d = plan.grad_dims[h], D = maxdeg[d];
+            const double* eta = plan.eta.data() + eta_off[d];
+            // Dm[b][k], b = 0..D, k = 0..D-1
+            std::vector<std::vector<ld>> Dm((size_t)D + 1, std::vector<ld>((size_t)D + 1, 0.0L));
+            for (int b = 1; b <= D; ++b) {
+                for (int k = 0; k < b - 1; ++k) {
+                    Dm[b][k + 1] += Dm[b - 1][k];
+                    Dm[b][k] += Dm[b - 1][k] * ((ld)eta[k] - (ld)eta[b - 1]);
+                }
+                Dm[b][b - 1] += 1.0L;
+            }
+            std::vector<ld>& out = Cd[h];
+            out.assign((size_t)T * d_out, 0.0L);
+            Key key2;
+            for (int32_t t = 1; t < T; ++t) {
+                const Key& key = term_key[t];
+                size_t pos = key.size();
+                for (size_t i = 0; i < key.size(); ++i)
+                    if (key[i] / kCode == d) pos = i;
+                if (pos == key.size()) continue;
+                const int b = (int)(key[pos] % kCode);
+                for (int k = 0; k < b; ++k) {
+                    const ld w = Dm[b][k];
+                    if (w == 0.0L) continue;
+                    key2 = key;
+                    if (k == 0) key2.erase(key2.begin() + pos);
+                    else key2[pos] = (int64_t)d * kCode + k;
+                    const auto it = term_id.find(key2);
+                    if (it == term_id.end()) return "internal error: index set is not downward closed";
+                    const ld* src = &C[(size_t)t * d_out];
+                    ld* dst = &out[(size_t)it->second * d_out];
+                    for (int64_t o = 0; o < d_out; ++o) dst[o] += w * src[o];
+                }
+            }
+        }
+    }
+    const int64_t n_gd = (int64_t)plan.grad_dims.size();
+    plan.n_sets = (int32_t)(d_out * (1 + n_gd));
+    // coefficient of term t in set s
+    auto coef_of = [&](int32_t t, int64_t set) -> double {
+        if (set < d_out) return (double)C[(size_t)t * d_out + set];
+        const int64_t o = (set - d_out) / n_gd, h = (set - d_out) % n_gd;
+        return (double)Cd[(size_t)h][(size_t)t * d_out + o];
+    };
+    plan.c0.resize((size_t)plan.n_sets);
+    for (int64_t set = 0; set < plan.n_sets; ++set) plan.c0[set] = coef_of(0, set);
 
     // ---- 8. value table: level-1 rows alias the hot entries, level >= 2 rows are appended level by level ---------
     const int32_t R = plan.n_rows;
@@ -457,8 +514,8 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
             Chunk ck;
             ck.block = b;
-            ck.flags = block_flags(b);
-            ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
+            ck.flags = block_flags(b) | (nch > 1 ? kChunkSplit : 0);
+            ck.coef.assign((r1 - r0) * (size_t)plan.n_sets * kBlockWidth, 0.0);
             // order the rows so that every group of four (one DMMA k-step) has four different table-row residues
             // modulo 4 as long as the item has them: with kTabPitch that makes the A-fragment loads conflict free
             std::vector<size_t> order;
@@ -474,8 +531,8 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
                 const size_t r = order[pos];
                 ck.rows.push_back(rows[r].first);
                 for (size_t q = rows[r].second.first; q < rows[r].second.second; ++q)
-                    for (int64_t o = 0; o < d_out; ++o)
-                        ck.coef[(pos * (size_t)d_out + o) * kBlockWidth + nz[q].lane] = (double)C[(size_t)nz[q].term * d_out + o];
+                    for (int64_t set = 0; set < plan.n_sets; ++set)
+                        ck.coef[(pos * (size_t)plan.n_sets + set) * kBlockWidth + nz[q].lane] = coef_of(nz[q].term, set);
             }
             chunks.push_back(std::move(ck));
         }
@@ -515,9 +572,9 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         // which (k-step, half block) pairs carry any coefficient at all (for any output): the others are skipped
         int32_t kmask = 0;
         for (int32_t r = 0; r < rows; ++r)
-            for (int64_t o = 0; o < d_out; ++o)
+            for (int64_t o = 0; o < plan.n_sets; ++o)
                 for (int i = 0; i < kBlockWidth; ++i)
-                    if (plan.coef[((size_t)(r0 + r) * d_out + o) * kBlockWidth + i] != 0.0) {
+                    if (plan.coef[((size_t)(r0 + r) * plan.n_sets + o) * kBlockWidth + i] != 0.0) {
                         // entry i belongs to n-tile j = (i >> 1) & 1 (lane mapping: entry = 4 * (n >> 1) + 2 * j + (n & 1))
                         kmask |= 1 << (2 * (r >> 2) + ((i >> 1) & 1));
                     }
@@ -540,6 +597,19 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
     for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
     if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
+
+    // ---- 11. nodes per dimension (the reference's gradient is NaN where a coordinate sits on one of them) -------------
+    {
+        std::vector<std::vector<double>> per_dim((size_t)d_in);
+        for (const PairInfo& pr : pairs) per_dim[pr.dim].insert(per_dim[pr.dim].end(), pr.nodes, pr.nodes + pr.deg + 1);
+        plan.nan_off.assign((size_t)d_in + 1, 0);
+        for (int64_t d = 0; d < d_in; ++d) {
+            std::sort(per_dim[d].begin(), per_dim[d].end());
+            per_dim[d].erase(std::unique(per_dim[d].begin(), per_dim[d].end()), per_dim[d].end());
+            plan.nan_nodes.insert(plan.nan_nodes.end(), per_dim[d].begin(), per_dim[d].end());
+            plan.nan_off[d + 1] = (int32_t)plan.nan_nodes.size();
+        }
+    }
     return "";
 }
 
@@ -569,10 +639,48 @@ void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ld
                 std::fill(acc.begin(), acc.end(), 0.0);
                 for (int32_t i = plan.chunk_off[c]; i < plan.chunk_off[c + 1]; ++i)
                     for (int64_t o = 0; o < d_out; ++o)
-                        acc[o] = std::fma(plan.coef[((size_t)i * d_out + o) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc[o]);
+                        acc[o] = std::fma(plan.coef[((size_t)i * plan.n_sets + o) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc[o]);
                 for (int64_t o = 0; o < d_out; ++o) yp[o] = std::fma(v, acc[o], yp[o]);
             }
         }
+    }
+}
+
+void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* J) {
+    const int64_t d_out = plan.d_out, d_in = plan.d_in, n_gd = (int64_t)plan.grad_dims.size();
+    std::vector<double> tab((size_t)plan.n_tab, 1.0);
+    std::vector<double> tot((size_t)plan.n_sets);
+    auto pi = [&](const double* xp, int32_t e) {
+        double v = 1.0;
+        for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
+        return v;
+    };
+    for (int64_t p = 0; p < N; ++p) {
+        const double* xp = x + p * ldx;
+        double* Jp = J + p * d_out * d_in;
+        std::fill(Jp, Jp + d_out * d_in, 0.0);
+        for (size_t e = 0; e < plan.ent_dim.size(); ++e)
+            if (plan.ent_tab[e] > 0) tab[plan.ent_tab[e]] = pi(xp, (int32_t)e);
+        for (int32_t t = 1 + plan.n_hot_rows; t < plan.n_tab; ++t)
+            tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot_rows]] * tab[plan.tab_hot[t - 1 - plan.n_hot_rows]];
+        for (int64_t s = 0; s < plan.n_sets; ++s) tot[s] = plan.c0[s];
+        for (int32_t c = 0; c < plan.n_chunks; ++c) {
+            const int32_t b = plan.chunk_block[c];
+            const bool hot = plan.chunk_flags[c] & kChunkHot;
+            for (int lane = 0; lane < kBlockWidth; ++lane) {
+                const int32_t e = b * kBlockWidth + lane;
+                const double v = hot ? tab[plan.ent_tab[e]] : pi(xp, e);
+                for (int64_t s = 0; s < plan.n_sets; ++s) {
+                    double acc = 0.0;
+                    for (int32_t i = plan.chunk_off[c]; i < plan.chunk_off[c + 1]; ++i)
+                        acc = std::fma(plan.coef[((size_t)i * plan.n_sets + s) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc);
+                    if (s < d_out && !hot && plan.ent_deg[e] > 0) Jp[s * d_in + plan.ent_dim[e]] += acc;  // cold dim: pi' = 1
+                    tot[s] = std::fma(v, acc, tot[s]);
+                }
+            }
+        }
+        for (int64_t o = 0; o < d_out; ++o)
+            for (int64_t h = 0; h < n_gd; ++h) Jp[o * d_in + plan.grad_dims[h]] = tot[d_out + o * n_gd + h];
     }
 }
 
@@ -633,5 +741,8 @@ void smxh_plan_stats(void* p, int64_t* out) {
 // Verification aid, CPU tests only (see smx_plan.h).
 void smxh_plan_eval_host(void* p, const double* x, int64_t N, int64_t ldx, double* y) {
     smx::eval_plan_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, y);
+}
+void smxh_plan_gradient_host(void* p, const double* x, int64_t N, int64_t ldx, double* J) {
+    smx::eval_plan_gradient_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, J);
 }
 }

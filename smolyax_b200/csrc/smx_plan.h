@@ -55,6 +55,7 @@ constexpr int kTabPitch = 36;      // doubles per value-table row in shared memo
 constexpr int kChunkHot = 1;      // all 16 entries are hot: their basis values are rows of the value table
 constexpr int kChunkContig = 2;   // 16 degree-1 entries on consecutive columns of x starting at an even column
 constexpr int kChunkInside = 4;   // .. and the 16 columns all exist (first column + 16 <= d_in)
+constexpr int kChunkSplit = 8;    // the block's rows are spread over more than one item
 
 struct FastPlan {
     int64_t d_in = 0, d_out = 0;
@@ -92,7 +93,15 @@ struct FastPlan {
     std::vector<int32_t> chunk_flags;
     std::vector<int32_t> chunk_off;      // size n_chunks+1, offsets into chunk_rows / coefficient row slots
     std::vector<int32_t> chunk_rows;     // value-table index of every row slot
-    std::vector<double> coef;
+    std::vector<double> coef;            // [row slot][set][kBlockWidth], n_sets coefficient sets per row slot:
+    int32_t n_sets = 0;                  //   set o < d_out: the interpolant's output o;
+    std::vector<int32_t> grad_dims;      //   set d_out + o * grad_dims.size() + h: d/dx_{grad_dims[h]} of output o (same terms,
+                                         //   coefficients mapped through the derivative of the Newton basis); the hot
+                                         //   dimensions with an entry.  Cold dimensions need no set: their derivative is the
+                                         //   row sum acc[p][e] itself (pi_e = x - eta_0).
+    // per dimension, the nodes at which the reference's gradient is NaN (barycentric.py:152-154): CSR over dimensions
+    std::vector<int32_t> nan_off;
+    std::vector<double> nan_nodes;
     // the same information packed for the kernel: one directory entry and one metadata record per work item
     std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags | kmask << 8, first column of x
     std::vector<int32_t> chunk_kmask;    // bit 2 s + j set: k-step s has a non-zero coefficient in entries 8 j .. 8 j + 7
@@ -113,10 +122,12 @@ inline int32_t hot_row(int32_t h) { return (h & ~15) | ((h & 3) << 2) | ((h >> 2
 
 // Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
-                            FastPlan& plan);
+                            FastPlan& plan, bool with_gradient = true);
 
 // Verification aid for the CPU-only test-suite: evaluates the plan on the host in fp64 in the same order as
 // the kernel.  NOT a product path — nothing in smolyax_b200/ calls it; see tests/test_plan.py.
 void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y);
+// same for the gradient sets: J (N, d_out, d_in), finite at nodes
+void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* J);
 
 }  // namespace smx

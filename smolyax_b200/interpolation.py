@@ -61,7 +61,7 @@ class SmolyakBarycentricInterpolator:
     # ------------------------------------------------------------------ construction (interpolation.py:51-113)
     def __init__(self, node_gen=None, k: Sequence[float] = None, d_out: int = None, t: float = None,
                  f: Callable = None, *, n_inputs: int = None, memory_limit: float = 4.0, method: str = "auto",
-                 device: int = None, batched_f: bool = False) -> None:
+                 device: int = None, batched_f: bool = False, nan_at_nodes: bool = True) -> None:
         r"""
         Parameters (all accepted as keywords, as in the reference)
         ----------
@@ -86,6 +86,9 @@ class SmolyakBarycentricInterpolator:
             CUDA ordinal (default: the current torch device).
         batched_f : bool
             If true ``set_f`` calls ``f`` once with all new nodes ``(n_new, d_in)`` instead of once per node.
+        nan_at_nodes : bool
+            ``gradient`` returns ``NaN`` in a dimension whose coordinate sits exactly on an interpolation node, as the
+            reference does (default).  ``False`` returns the true, finite derivative there (fast path only).
         """
         assert node_gen is not None and k is not None and d_out is not None and t is not None
         assert method in ("auto", "barycentric")
@@ -98,6 +101,7 @@ class SmolyakBarycentricInterpolator:
         self._method = method
         self._device = (torch.cuda.current_device() if torch.cuda.is_available() else 0) if device is None else int(device)
         self._batched_f = batched_f
+        self._nan_at_nodes = nan_at_nodes
         self._memory_limit = memory_limit
         self._n_inputs = n_inputs
 
@@ -131,6 +135,7 @@ class SmolyakBarycentricInterpolator:
         self._layout = layout
         self._release()
         flags = _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
+        flags |= 0 if self._nan_at_nodes else _lib.SMX_GRAD_FINITE_AT_NODES
         with torch.cuda.device(self._device):
             self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
 

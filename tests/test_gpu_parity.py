@@ -81,6 +81,30 @@ def test_gradient(case):
 
 
 @pytest.mark.parametrize("case", ALL_CASES)
+def test_gradient_barycentric_kernels_and_finite_option(case):
+    """The per-summand gradient kernels (method="barycentric") against the oracle, and the fast gradient with
+    nan_at_nodes=False: finite everywhere, equal to the default result wherever that one is not NaN."""
+    from oracle import oracle
+
+    g, ip = _build(case, method="barycentric")
+    J_ref = g["J_ref"]
+    x = g["x"][: len(J_ref)]
+    J = ip.gradient(x)
+    J_orc = oracle.gradient(ip.reference_layout(), x)
+    assert np.array_equal(np.isnan(J), np.isnan(J_orc))
+    ok = ~np.isnan(J_orc)
+    scale = max(1.0, float(np.max(np.abs(J_orc[ok])))) if ok.any() else 1.0
+    assert np.max(np.abs(J[ok] - J_orc[ok]), initial=0.0) <= 1e-10 * scale
+    _, fin = _build(case, nan_at_nodes=False)
+    Jf = fin.gradient(x)
+    assert np.isfinite(Jf).all()
+    J_ld = long_double(g, "J")
+    err_new = np.max(np.abs((Jf - J_ld)[ok].astype(float)), initial=0.0) / scale
+    err_ref = np.max(np.abs((J_ref - J_ld)[ok].astype(float)), initial=0.0) / scale
+    assert err_new <= max(err_ref, 1e-12)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
 def test_integral(case):
     g, ip = _build(case)
     Q = ip.integral()
