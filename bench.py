@@ -41,36 +41,46 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while the timed region runs (NVML is initialised up front so
+    that the first sample falls inside the region)."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.nv, self.handle = [], set(), None, None, None
         self._stop_evt = threading.Event()
-
-    def run(self):
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {
-                nv.nvmlClocksEventReasonSwPowerCap if hasattr(nv, "nvmlClocksEventReasonSwPowerCap") else 0x4: "sw_power_cap",
-                0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake",
-            }
-            while not self._stop_evt.is_set():
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.0005)
+            self.nv, self.handle = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self._sample()  # warm the NVML path; discarded below
+            self.samples.clear()
         except Exception as exc:  # NVML missing: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def _sample(self):
+        nv, h = self.nv, self.handle
+        self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self._sample()
+            except Exception as exc:
+                self.reasons.add(f"nvml_error:{type(exc).__name__}")
+                return
 
     def stop(self):
         self._stop_evt.set()
@@ -181,10 +191,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         y = ip(x)
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
     launches0 = _lib.lib.smx_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
