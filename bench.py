@@ -89,12 +89,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference(wl, layout, seconds: float, repeats: int):
+ORACLE_COLUMNS = 64  # outputs the CPU oracle evaluates when the padded reference layout of all d_out would not fit
+
+
+def oracle_layout(wl):
+    """Reference layout (the oracle's input) of the workload; for huge d_out restricted to ORACLE_COLUMNS evenly spaced
+    output columns (the padded F_n of all 10^4 outputs of cfg3 would be 29 GB).  Returns (layout, columns or None)."""
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    cols = None
+    fam = wl.target()
+    f = fam
+    if wl.d_out > 256:
+        cols = np.unique(np.linspace(0, wl.d_out - 1, ORACLE_COLUMNS).astype(np.int64))
+        f = lambda x: fam(x)[..., cols]  # noqa: E731
+    ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), layout="reference", batched_f=True,
+                                        d_out=wl.d_out if cols is None else len(cols))
+    return ip._assemble(f, {})[0], cols
+
+
+def cpu_reference(wl, layout, seconds: float, repeats: int, cols=None):
     """Times the oracle (plain-C restatement of the reference algorithm, OpenMP over points) on the host cores on a
     bounded sample of the workload.  Returns (points*d_out/s, cores, sample description, per-repeat seconds)."""
     from oracle import oracle
 
     cores = oracle.use_all_cores()
+    d_eff = wl.d_out if cols is None else len(cols)
     x = wl.points(max(cores * 4, 32), seed=123)
     t0 = time.perf_counter()
     oracle.evaluate(layout, x)
@@ -107,7 +127,8 @@ def cpu_reference(wl, layout, seconds: float, repeats: int):
         oracle.evaluate(layout, x)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return n * wl.d_out / best, cores, f"{n} points of the same workload, best of {repeats} ({best:.2f} s each)", times
+    what = "the same workload" if cols is None else f"the same workload restricted to {d_eff} of its {wl.d_out} outputs"
+    return n * d_eff / best, cores, f"{n} points of {what}, best of {repeats} ({best:.2f} s each)", times
 
 
 def run_reference(args):
@@ -118,11 +139,10 @@ def run_reference(args):
     from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
 
     wl = workloads.CONFIGS[args.config]
-    ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out)
-    layout, _ = ip._assemble(wl.target(), {})
+    layout, cols = oracle_layout(wl)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference(wl, layout, 0.5, 1)
-    value, cores, sample, times = cpu_reference(wl, layout, args.cpu_seconds, max(1, min(args.steps, 3)))
+        cpu_reference(wl, layout, 0.5, 1, cols)
+    value, cores, sample, times = cpu_reference(wl, layout, args.cpu_seconds, max(1, min(args.steps, 3)), cols)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * min(times), "higher_is_better": True, "scaling": "weak",
@@ -142,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--points", type=int, default=0, help="points per GPU (default: the config's batch)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -171,8 +191,10 @@ def main():
     d_in, d_out = wl.d_in, wl.d_out
 
     # ---- set-up: rank 0 evaluates f and assembles the tables once, NCCL broadcast, one device handle per rank ----
-    ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=d_out, device=local)
-    layout = ip._assemble(wl.target(), {})[0] if rank == 0 else None
+    ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=d_out, device=local,
+                                        batched_f=True)
+    compact = d_out > 256  # the padded reference layout of cfg3 (29 GB) cannot be assembled: smx_create_compact
+    layout = (ip._assemble_compact if compact else ip._assemble)(wl.target(), {})[0] if rank == 0 else None
     layout = sdist.broadcast_layout(layout, src=0)
     ip.set_layout(layout)
     info = ip.device_info()
@@ -214,9 +236,11 @@ def main():
     if rank == 0:
         from oracle import oracle
 
+        check_layout, cols = (layout, None) if not compact else oracle_layout(wl)
         xs = x[:64].cpu().numpy()
-        ref = oracle.evaluate(layout, xs)
-        parity = float(np.max(np.abs(y[:64].cpu().numpy() - ref) / np.maximum(np.abs(ref), 1e-300)))
+        ref = oracle.evaluate(check_layout, xs)
+        got = y[:64].cpu().numpy()
+        parity = float(np.max(np.abs((got if cols is None else got[:, cols]) - ref) / np.maximum(np.abs(ref), 1e-300)))
 
     # ---- end to end through the public API from pinned host memory ------------------------------------------------
     x_host = torch.empty((n_points, d_in), dtype=torch.float64, pin_memory=True)
@@ -242,12 +266,34 @@ def main():
                 traffic = json.loads(tfile.read_text()).get(args.config)
             except Exception:
                 traffic = None
-        fp64_tflops = 2.0 * info["padded_fma"] * d_out * n_points / (ms_per_step * 1e-3) / 1e12
+        dense = bool(info["has_dense_path"])
+        fma_per_eval = info["dense_terms"] if dense else info["padded_fma"]
+        fp64_tflops = 2.0 * fma_per_eval * d_out * n_points / (ms_per_step * 1e-3) / 1e12
         fp64_peak = None
         try:
             fp64_peak = json.loads((ROOT / "profiles" / "fp64_peaks.json").read_text())["fp64_dmma_tflops"]
         except Exception:
             pass
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+            "kernel": "fast_eval_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+            "fp64_tflops_executed": fp64_tflops, "fp64_dmma_peak_tflops_measured": fp64_peak,
+            "note": "x is streamed once (8*(d_in+d_out) B per point); the FP64 tensor work (2*padded_fma flop per point) "
+                    "needs 0.94 ms per 1e6 points at the measured DMMA peak, the x stream 1.24 ms at the measured HBM peak",
+        }
+        if dense:
+            # GEMM regime (folded form): algorithmic flops = 2 * d_out * n_terms per point, on the FP64 tensor
+            # instruction; the denominator is the FP64 DMMA rate measured on this GPU type (profiles/fp64_peaks.json) -
+            # MEASURED_PEAKS.json only carries the bf16 tensor rate, which no fp64 path can use.
+            alg_flops = 2.0 * info["n_terms"] * d_out * n_points
+            tf = alg_flops / (ms_per_step * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
+                "traffic": traffic, "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) rate measured with profiles/fp64_peaks.cu",
+                "kernel": "dense_eval_kernel", "algorithmic_flops_per_launch": alg_flops,
+                "hbm_gbs_algorithmic": achieved, "hbm_peak_gbs": peaks["hbm_gbs"],
+            }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -256,16 +302,9 @@ def main():
                 "workload": f"{args.config}: {wl.rule} d_in={d_in} d_out={d_out} n={wl.n_target} "
                             f"({info['n_summands']} summands, {info['n_terms']} terms), {n_points} points per GPU",
                 "points_per_gpu": n_points, "parallelism": f"dp{world} (points sharded, tables replicated)",
-                "l2": "inputs (8 GB per step) exceed L2 (126 MB); no flush needed",
+                "l2": f"inputs + outputs ({8e-9 * (d_in + d_out) * n_points:.1f} GB per step) exceed L2 (126 MB); no flush needed",
             },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel": "fast_eval_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                "fp64_tflops_executed": fp64_tflops, "fp64_dmma_peak_tflops_measured": fp64_peak,
-                "note": "x is streamed once (8*(d_in+d_out) B per point); the FP64 tensor work (2*padded_fma flop per point) "
-                        "needs 0.94 ms per 1e6 points at the measured DMMA peak, the x stream 1.24 ms at the measured HBM peak",
-            },
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * d_in * n_points,
                     "d2h_bytes_per_step": 8 * d_out * n_points, "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
             "gpu_launches": launches,
@@ -273,7 +312,8 @@ def main():
             "parity_max_rel_vs_oracle_first64": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_reference(wl, layout, args.cpu_seconds, 1)
+            cpu_layout, cpu_cols = (layout, None) if not compact else oracle_layout(wl)
+            v, cores, sample, _ = cpu_reference(wl, cpu_layout, args.cpu_seconds, 1, cpu_cols)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -23,7 +23,8 @@ from smolyax_b200.interpolation import SmolyakBarycentricInterpolator  # noqa: E
 
 # (config, d_out override, eval points, gradient points)
 CASES = [("cfg1", None, 10_000, 10_000), ("cfg2", None, 1_000_000, 2_000), ("cfg3", 64, 100_000, 2_000),
-         ("cfg4", None, 100_000, 1_000), ("cfg5", None, 100_000, 200)]
+         ("cfg3", None, 100_000, 0), ("cfg4", None, 100_000, 1_000), ("cfg5", None, 1_000_000, 200)]
+DMMA_PEAK_TFLOPS = 37.12  # profiles/fp64_peaks.json
 
 
 def timed(fn, reps):
@@ -49,13 +50,14 @@ def main():
     args = ap.parse_args()
     lines = []
     for name, d_out, n_eval, n_grad in CASES:
-        if args.only and name not in args.only.split(","):
+        if args.only and name not in args.only.split(",") and f"{name}:{d_out}" not in args.only.split(","):
             continue
         wl = workloads.CONFIGS[name]
         if d_out is not None:
             wl = workloads.Workload(name, wl.rule, wl.d_in, d_out, wl.n_target, wl.n_points)
         t0 = time.perf_counter()
-        ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out, f=wl.target())
+        ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out, f=wl.target(),
+                                            batched_f=True)
         setup_s = time.perf_counter() - t0
         info = ip.device_info()
         gen = torch.Generator(device="cuda").manual_seed(0)
@@ -64,15 +66,28 @@ def main():
         base = {"config": name, "rule": wl.rule, "d_in": wl.d_in, "d_out": wl.d_out, "n_f_evals": ip.n_f_evals,
                 "summands": info["n_summands"], "terms": info["n_terms"], "setup_s": round(setup_s, 2)}
         ms = timed(lambda: ip(x), args.reps)
-        lines.append({**base, "op": "eval", "points": n_eval, "ms": ms, "value": n_eval * wl.d_out / ms * 1e3, "unit": "points*d_out/s",
-                      "hbm_gbs_algorithmic": 8.0 * (wl.d_in + wl.d_out) * n_eval / ms / 1e6})
-        xg = x[:n_grad]
-        ms = timed(lambda: ip.gradient(xg), max(2, args.reps // 2))
-        lines.append({**base, "op": "gradient", "points": n_grad, "ms": ms, "value": n_grad * wl.d_out * wl.d_in / ms * 1e3,
-                      "unit": "J entries/s", "points_per_s": n_grad / ms * 1e3})
+        first = len(lines)
+        tf = 2.0 * info["n_terms"] * wl.d_out * n_eval / ms / 1e9
+        lines.append({**base, "op": "eval", "kernel": "dense" if info["has_dense_path"] else "sparse", "points": n_eval, "ms": ms,
+                      "value": n_eval * wl.d_out / ms * 1e3, "unit": "points*d_out/s",
+                      "hbm_gbs_algorithmic": 8.0 * (wl.d_in + wl.d_out) * n_eval / ms / 1e6,
+                      "tflops_algorithmic": tf, "frac_of_fp64_dmma_peak": tf / DMMA_PEAK_TFLOPS})
+        if info["has_dense_path"] and wl.d_out <= 2048:  # the same tables through the block-sparse kernel, for comparison
+            alt = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out, dense=False)
+            alt.set_layout(ip._layout)
+            xa = x[: max(n_eval // 10, 1000)]
+            ms_a = timed(lambda: alt(xa), max(2, args.reps // 2))
+            lines.append({**base, "op": "eval", "kernel": "sparse", "points": len(xa), "ms": ms_a,
+                          "value": len(xa) * wl.d_out / ms_a * 1e3, "unit": "points*d_out/s"})
+            del alt
+        if n_grad:
+            xg = x[:n_grad]
+            ms = timed(lambda: ip.gradient(xg), max(2, args.reps // 2))
+            lines.append({**base, "op": "gradient", "points": n_grad, "ms": ms, "value": n_grad * wl.d_out * wl.d_in / ms * 1e3,
+                          "unit": "J entries/s", "points_per_s": n_grad / ms * 1e3})
         ms = timed(lambda: ip.integral(), args.reps)
         lines.append({**base, "op": "integral", "ms": ms, "value": 1e3 / ms, "unit": "calls/s"})
-        for ln in lines[-3:]:
+        for ln in lines[first:]:
             print(json.dumps(ln), flush=True)
         del ip, x
         torch.cuda.empty_cache()

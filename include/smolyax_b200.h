@@ -58,6 +58,9 @@ typedef struct {
 #define SMX_GRAD_FINITE_AT_NODES 4u /* fast gradient: return the true (finite) derivative where a coordinate sits on a
                                        node, instead of the NaN the reference produces there (barycentric.py:152-154) */
 
+#define SMX_DENSE_PATH 8u     /* build the GEMM-regime form (dense term matrix, FP64 tensor instruction) even for small d_out */
+#define SMX_NO_DENSE_PATH 16u /* never build it; default: built when d_out >= 32 (DESIGN.md "K2") */
+
 typedef struct {
     int64_t d_in;
     int64_t d_out;
@@ -67,12 +70,45 @@ typedef struct {
     uint32_t flags;
 } smx_interp_desc;
 
+/*
+ * The same interpolant WITHOUT the reference's zero padding and without repeating shared function values: what
+ * set_f (interpolation.py:115-239) knows before it pads.  The padded F_n of the named configuration
+ * "d_in = 100, d_out = 10^4, n = 10^4" would be 29 GB of host memory; this form of it is 0.8 GB.
+ *   summand s (multi-index with zeta != 0, n_active[s] >= 1 active dimensions) owns slots
+ *   [slot_off[s], slot_off[s+1]):  dims / degs per slot (any order inside the summand), node_off = offset of the
+ *   slot's deg+1 nodes in node_pool (and of its deg+1 quadrature weights in quad_pool, optional);
+ *   its value tensor has shape (deg_1+1, .., deg_n+1) in slot order, C order; entry i of it is row
+ *   val_index[val_off[s] + i] of `values` (n_values, d_out) - for nested rules one row per sparse-grid node
+ *   (= one evaluation of f, interpolation.py:160-163, 217-224), shared by every summand that contains the node.
+ * All pointers are HOST pointers.
+ */
+typedef struct {
+    int64_t n_summands;
+    const int32_t* n_active;  /* (n_summands) */
+    const int64_t* slot_off;  /* (n_summands + 1) */
+    const int64_t* dims;      /* (slots) */
+    const int64_t* degs;      /* (slots) */
+    const int64_t* node_off;  /* (slots) */
+    const double* node_pool;
+    const double* quad_pool;  /* NULL: smx_integral is not available on the handle */
+    const int64_t* zetas;     /* (n_summands) */
+    const int64_t* val_off;   /* (n_summands + 1) */
+    const int64_t* val_index;
+    const double* values;     /* (n_values, d_out) row-major */
+    int64_t n_values;
+} smx_compact_desc;
+
 typedef struct smx_interp smx_interp; /* opaque; owns every device table it needs */
 
 /* ---- life cycle ------------------------------------------------------------------------------------------
  * smx_create replaces the upload at interpolation.py:230-235: it takes the reference-layout HOST arrays and
  * re-packs them into the device layout (DESIGN.md "Data layout in HBM").  device = CUDA ordinal (-1: current). */
 int smx_create(const smx_interp_desc* desc, int device, smx_interp** out);
+/* Same from the compact description.  The handle serves smx_eval, smx_gradient (when the derivative sets fit, else
+ * SMX_ERR_UNSUPPORTED) and smx_integral (evaluated once at create time, in extended precision on the host: it does not
+ * depend on x).  flags: SMX_GRAD_FINITE_AT_NODES, SMX_DENSE_PATH, SMX_NO_DENSE_PATH. */
+int smx_create_compact(int64_t d_in, int64_t d_out, const double* offset, const smx_compact_desc* desc, uint32_t flags,
+                       int device, smx_interp** out);
 int smx_destroy(smx_interp* h);
 
 /* ---- the path --------------------------------------------------------------------------------------------
@@ -126,6 +162,8 @@ typedef struct {
     int64_t padded_fma;     /* fast path: lane-FMAs per point and output in the block-sparse contraction */
     int64_t device_bytes;   /* HBM held by the handle */
     int32_t has_fast_path, has_groups, nested;
+    int32_t has_dense_path; /* GEMM-regime form present: smx_eval uses it */
+    int64_t dense_terms;    /* its K (terms, padded to whole k-steps of 4) */
 } smx_info;
 int smx_get_info(const smx_interp* h, smx_info* info);
 

@@ -15,6 +15,8 @@ from . import _build
 SMX_KEEP_GROUPS = 1
 SMX_NO_FAST_PATH = 2
 SMX_GRAD_FINITE_AT_NODES = 4
+SMX_DENSE_PATH = 8
+SMX_NO_DENSE_PATH = 16
 
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "out of device memory", 4: "unsupported shape", 5: "no sm_100 device"}
 
@@ -49,14 +51,25 @@ class InterpDesc(ctypes.Structure):
     ]
 
 
+COMPACT_FIELDS = (("n_active", np.int32), ("slot_off", np.int64), ("dims", np.int64), ("degs", np.int64),
+                  ("node_off", np.int64), ("node_pool", np.float64), ("quad_pool", np.float64), ("zetas", np.int64),
+                  ("val_off", np.int64), ("val_index", np.int64), ("values", np.float64))
+
+
+class CompactDesc(ctypes.Structure):
+    _fields_ = [("n_summands", c_int64)] + [(name, c_void_p) for name, _ in COMPACT_FIELDS] + [("n_values", c_int64)]
+
+
 class Info(ctypes.Structure):
     _fields_ = [(name, c_int64) for name in (
         "d_in", "d_out", "n_summands", "w_raw", "w_pad", "n_terms", "n_entries", "n_rows", "n_chunks", "padded_fma",
-        "device_bytes")] + [(name, c_int32) for name in ("has_fast_path", "has_groups", "nested")]
+        "device_bytes")] + [(name, c_int32) for name in ("has_fast_path", "has_groups", "nested", "has_dense_path")] + [
+        ("dense_terms", c_int64)]
 
 
 EXPORTS = {
     "smx_create": (c_int, [POINTER(InterpDesc), c_int, POINTER(c_void_p)]),
+    "smx_create_compact": (c_int, [c_int64, c_int64, c_void_p, POINTER(CompactDesc), c_uint32, c_int, POINTER(c_void_p)]),
     "smx_destroy": (c_int, [c_void_p]),
     "smx_eval": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "smx_gradient": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -137,6 +150,33 @@ def create(layout, d_in: int, d_out: int, flags: int, device: int = -1):
     desc = InterpDesc(d_in, d_out, off.ctypes.data, n_groups, arr, flags)
     handle = c_void_p()
     check(lib.smx_create(ctypes.byref(desc), device, ctypes.byref(handle)), "smx_create")
+    del keep
+    return handle
+
+
+def pack_compact(layout):
+    """smx_compact_desc for a compact layout dict (interpolation._assemble_compact); returns (desc, keepalive)."""
+    desc = CompactDesc()
+    keep = []
+    desc.n_summands = len(layout["zetas"])
+    for name, dt in COMPACT_FIELDS:
+        a = layout.get(name)
+        if a is None:
+            setattr(desc, name, None)
+            continue
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        setattr(desc, name, a.ctypes.data)
+    desc.n_values = layout["values"].shape[0]
+    return desc, keep
+
+
+def create_compact(layout, d_in: int, d_out: int, flags: int, device: int = -1):
+    desc, keep = pack_compact(layout)
+    off = np.ascontiguousarray(np.broadcast_to(np.asarray(layout["offset"], dtype=np.float64), (d_out,)))
+    handle = c_void_p()
+    check(lib.smx_create_compact(d_in, d_out, off.ctypes.data, ctypes.byref(desc), flags, device, ctypes.byref(handle)),
+          "smx_create_compact")
     del keep
     return handle
 

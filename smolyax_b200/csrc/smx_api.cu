@@ -1,4 +1,5 @@
 // C-ABI of include/smolyax_b200.h: handle life cycle, dispatch to the kernels, host-buffer pipeline.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -29,7 +30,8 @@ struct smx_interp {
     int device = 0;
     int64_t d_in = 0, d_out = 0;
     smx_info info{};
-    bool has_fast = false, has_groups = false, grad_finite = false;
+    bool has_fast = false, has_groups = false, grad_finite = false, compact = false;
+    double* d_integral = nullptr;  // compact handles: the integral, computed at create time
     FastDevice fast;
     std::vector<SeamGroup> groups;
     std::vector<void*> owned;  // device allocations behind `groups`
@@ -83,6 +85,7 @@ void release(smx_interp* h) {
     fast_free(h->fast);
     for (void* p : h->owned) cudaFree(p);
     if (h->d_offset) cudaFree(h->d_offset);
+    if (h->d_integral) cudaFree(h->d_integral);
     if (h->integral_ws) cudaFree(h->integral_ws);
     for (int i = 0; i < smx_interp::kStages; ++i) {
         if (h->stage_x[i]) cudaFree(h->stage_x[i]);
@@ -107,9 +110,96 @@ int ensure_stages(smx_interp* h, int64_t points, int64_t ldx) {
     return SMX_OK;
 }
 
+PlanOptions plan_options(uint32_t flags, int64_t d_out, bool sparse_wanted) {
+    PlanOptions opt;
+    static const int dense_min = std::getenv("SMX_DENSE_MIN") ? std::atoi(std::getenv("SMX_DENSE_MIN")) : 32;
+    opt.dense = (flags & SMX_DENSE_PATH) || (!(flags & SMX_NO_DENSE_PATH) && d_out >= dense_min);
+    // the block-sparse form stores every coefficient set padded to 16-entry blocks: beyond a few thousand outputs it
+    // only costs memory once the dense form exists (it would still serve the gradient)
+    opt.sparse = sparse_wanted && !(opt.dense && d_out > 2048);
+    opt.gradient = opt.sparse;
+    return opt;
+}
+
+// plan -> device tables; fills the statistics of the handle
+int adopt_plan(smx_interp* h, const FastPlan& plan) {
+    h->info.n_summands = plan.n_summands;
+    h->info.w_raw = plan.w_raw;
+    h->info.w_pad = plan.w_pad;
+    h->info.n_terms = plan.n_terms;
+    h->info.n_entries = plan.n_entries;
+    h->info.n_rows = plan.n_rows;
+    h->info.n_chunks = plan.n_chunks;
+    h->info.padded_fma = plan.padded_fma;
+    h->info.nested = plan.nested ? 1 : 0;
+    const int rc = fast_upload(plan, h->fast);
+    if (rc) return rc;
+    h->has_fast = true;
+    h->info.device_bytes += h->fast.bytes;
+    h->info.has_dense_path = h->fast.has_dense;
+    h->info.dense_terms = 4ll * h->fast.dense_k4;
+    return SMX_OK;
+}
+
+int upload_offset(smx_interp* h, const double* offset) {
+    std::vector<double> off((size_t)h->d_out, 0.0);
+    if (offset) std::memcpy(off.data(), offset, sizeof(double) * h->d_out);
+    SMX_CUDA(cudaMalloc((void**)&h->d_offset, sizeof(double) * h->d_out));
+    SMX_CUDA(cudaMemcpy(h->d_offset, off.data(), sizeof(double) * h->d_out, cudaMemcpyHostToDevice));
+    h->info.device_bytes += (int64_t)sizeof(double) * h->d_out;
+    return SMX_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int smx_create_compact(int64_t d_in, int64_t d_out, const double* offset, const smx_compact_desc* desc, uint32_t flags,
+                       int device, smx_interp** out) {
+    if (!desc || !out) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: null argument");
+    *out = nullptr;
+    if (d_in <= 0 || d_out <= 0) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: d_in and d_out must be positive");
+    int dev = 0, rc;
+    if ((rc = check_device(device, &dev))) return rc;
+    std::unique_ptr<smx_interp, void (*)(smx_interp*)> h(new smx_interp(), release);
+    h->device = dev;
+    h->d_in = h->info.d_in = d_in;
+    h->d_out = h->info.d_out = d_out;
+    h->compact = true;
+    h->grad_finite = (flags & SMX_GRAD_FINITE_AT_NODES) != 0;
+    CompactView cv;
+    cv.n_summands = desc->n_summands;
+    cv.n_active = desc->n_active;
+    cv.slot_off = desc->slot_off;
+    cv.dims = desc->dims;
+    cv.degs = desc->degs;
+    cv.node_off = desc->node_off;
+    cv.node_pool = desc->node_pool;
+    cv.quad_pool = desc->quad_pool;
+    cv.zetas = desc->zetas;
+    cv.val_off = desc->val_off;
+    cv.val_index = desc->val_index;
+    cv.values = desc->values;
+    cv.n_values = desc->n_values;
+    {
+        FastPlan plan;
+        const std::string err = build_fast_plan_compact(d_in, d_out, offset, cv, plan, plan_options(flags, d_out, true));
+        if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: " + err);
+        if ((rc = adopt_plan(h.get(), plan))) return rc;
+    }
+    if (desc->quad_pool || desc->n_summands == 0) {
+        std::vector<double> Q;
+        const std::string err = integrate_compact(d_out, offset, cv, Q);
+        if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: " + err);
+        SMX_CUDA(cudaMalloc((void**)&h->d_integral, sizeof(double) * d_out));
+        SMX_CUDA(cudaMemcpy(h->d_integral, Q.data(), sizeof(double) * d_out, cudaMemcpyHostToDevice));
+        h->info.device_bytes += (int64_t)sizeof(double) * d_out;
+    }
+    if ((rc = upload_offset(h.get(), offset))) return rc;
+    h->info.has_fast_path = 1;
+    *out = h.release();
+    return SMX_OK;
+}
 
 int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
     if (!desc || !out) return fail(SMX_ERR_INVALID_ARG, "smx_create: null argument");
@@ -149,26 +239,14 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
     bool want_groups = (desc->flags & SMX_KEEP_GROUPS) != 0 || !want_fast;
     if (want_fast) {
         FastPlan plan;
-        const std::string err = build_fast_plan(desc->d_in, desc->d_out, desc->offset, views, plan);
+        const std::string err = build_fast_plan(desc->d_in, desc->d_out, desc->offset, views, plan, plan_options(desc->flags, desc->d_out, true));
         if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create: " + err);
-        h->info.n_summands = plan.n_summands;
-        h->info.w_raw = plan.w_raw;
-        h->info.w_pad = plan.w_pad;
-        h->info.n_terms = plan.n_terms;
-        h->info.n_entries = plan.n_entries;
-        h->info.n_rows = plan.n_rows;
-        h->info.n_chunks = plan.n_chunks;
-        h->info.padded_fma = plan.padded_fma;
-        h->info.nested = plan.nested ? 1 : 0;
-        rc = fast_upload(plan, h->fast);
+        rc = adopt_plan(h.get(), plan);
         if (rc == SMX_ERR_UNSUPPORTED) {
             fast_free(h->fast);  // fall back to the per-summand kernels; still a CUDA path
             want_groups = true;
         } else if (rc) {
             return rc;
-        } else {
-            h->has_fast = true;
-            h->info.device_bytes += h->fast.bytes;
         }
     }
     if (want_groups) {
@@ -196,13 +274,7 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
         }
         h->has_groups = true;
     }
-    {
-        std::vector<double> off((size_t)desc->d_out, 0.0);
-        if (desc->offset) std::memcpy(off.data(), desc->offset, sizeof(double) * desc->d_out);
-        SMX_CUDA(cudaMalloc((void**)&h->d_offset, sizeof(double) * desc->d_out));
-        SMX_CUDA(cudaMemcpy(h->d_offset, off.data(), sizeof(double) * desc->d_out, cudaMemcpyHostToDevice));
-        h->info.device_bytes += (int64_t)sizeof(double) * desc->d_out;
-    }
+    if ((rc = upload_offset(h.get(), desc->offset))) return rc;
     h->info.has_fast_path = h->has_fast;
     h->info.has_groups = h->has_groups;
     *out = h.release();
@@ -225,7 +297,8 @@ int smx_eval(smx_interp* h, const double* x, int64_t N, int64_t ldx, double* y, 
     if (N == 0) return SMX_OK;
     if (!x || !y || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_eval: null buffer or ldx < d_in");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->has_fast) return fast_eval(h->fast, x, N, ldx, y, st);
+    if (h->has_fast && h->fast.has_dense) return dense_eval(h->fast, x, N, ldx, y, st);
+    if (h->has_fast && h->fast.has_sparse) return fast_eval(h->fast, x, N, ldx, y, st);
     int rc;
     if ((rc = fill_rows(y, N, h->d_out, h->d_offset, st))) return rc;
     for (const SeamGroup& g : h->groups)
@@ -238,7 +311,9 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
     if (N == 0) return SMX_OK;
     if (!x || !J || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: null buffer or ldx < d_in");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->has_fast && h->fast.grad_ok) return fast_gradient(h->fast, x, N, ldx, J, !h->grad_finite, st);
+    if (h->has_fast && h->fast.has_sparse && h->fast.grad_ok) return fast_gradient(h->fast, x, N, ldx, J, !h->grad_finite, st);
+    if (h->compact)
+        return fail(SMX_ERR_UNSUPPORTED, "smx_gradient: the derivative coefficient sets of this handle were not built (d_out too large)");
     if (!h->has_groups && h->info.n_summands > 0)
         return fail(SMX_ERR_INVALID_ARG, "smx_gradient: no derivative sets and no reference layout (SMX_KEEP_GROUPS) on this handle");
     SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * h->d_out * h->d_in, st));
@@ -250,6 +325,11 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
 
 int smx_integral(smx_interp* h, double* q, void* stream) {
     if (!h || !q) return fail(SMX_ERR_INVALID_ARG, "smx_integral: null argument");
+    if (h->compact) {
+        if (!h->d_integral) return fail(SMX_ERR_INVALID_ARG, "smx_integral: handle was created without quadrature weights");
+        SMX_CUDA(cudaMemcpyAsync(q, h->d_integral, sizeof(double) * h->d_out, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        return SMX_OK;
+    }
     if (!h->has_groups && h->info.n_summands > 0)
         return fail(SMX_ERR_INVALID_ARG, "smx_integral: handle was created without SMX_KEEP_GROUPS");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -272,7 +352,7 @@ int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, d
     SMX_CUDA(cudaSetDevice(h->device));
     if (chunk_points <= 0) {
         // ~64 MiB of x per stage keeps the copy engines and the SMs busy at the same time
-        chunk_points = std::max<int64_t>(1024, (64ll << 20) / (int64_t)(h->d_in * sizeof(double)));
+        chunk_points = std::max<int64_t>(1024, (64ll << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
     }
     chunk_points = std::min(chunk_points, N);
     int rc;

@@ -87,6 +87,12 @@ struct FastDevice {
     int32_t* grad_dims = nullptr;
     int32_t* nan_off = nullptr;     // per dimension: the nodes at which the reference returns NaN gradients
     double* nan_nodes = nullptr;
+    // GEMM-regime form (large d_out): dense term matrix in DMMA fragment order, see smx_plan.h
+    bool has_sparse = false, has_dense = false;
+    int32_t dense_k4 = 0;
+    int32_t* dense_meta = nullptr;
+    double* dense_eta0 = nullptr;
+    double* dense_coef = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
@@ -94,6 +100,7 @@ struct FastDevice {
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);
 int fast_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
+int dense_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
 int fast_gradient(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st);
 
 }  // namespace smx

@@ -1,0 +1,28 @@
+// Definitions shared by the host side (smx_fast.cu) and the GEMM-regime kernel (smx_dense_kernel.cu).
+#pragma once
+#include "smx_common.cuh"
+
+namespace smx {
+
+constexpr int kDenseTile = 32;  // points per CTA
+
+struct DenseArgs {
+    const double* eta;
+    const int2* tab_pairs;   // value-table rows of level >= 2: (parent row, hot row)
+    const int32_t* hot_off;
+    const int32_t* hot_pos;
+    const int2* meta;        // per term: (table row of the hot part, table row of the leading entry or -1 - column of x)
+    const double* eta0;      // (d_in) first centre of every dimension
+    const double* coef;      // [ceil(d_out / 8)][k4][32] DMMA B fragments
+    const double* c0;
+    long long N, ldx, d_out;
+    int k4;                  // k-steps (4 terms each)
+    int nblk;                // ceil(d_out / 8)
+    int n_tab, n_hot_rows, n_levels, hot_dims;
+    int level_off[kMaxLevels + 2];
+};
+
+bool dense_kernel_fits(int n_tab, int smem_optin);
+int dense_kernel_launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st);
+
+}  // namespace smx

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "smx_dense.cuh"
 #include "smx_fast_common.cuh"
 
 namespace smx {
@@ -60,14 +61,37 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     dev.n_flat = (int32_t)(plan.tab_factors.size() / 4);
     if (plan.n_levels > kMaxLevels) return fail(SMX_ERR_UNSUPPORTED, "too many active dimensions per term");
     for (size_t l = 0; l < plan.level_off.size() && l < (size_t)kMaxLevels + 2; ++l) dev.level_off[l] = plan.level_off[l];
+    bool sparse_ok = plan.has_sparse;
     for (int32_t c = 0; c < plan.n_chunks; ++c)
-        if (!(plan.chunk_flags[c] & (kChunkHot | kChunkContig)))
-            return fail(SMX_ERR_UNSUPPORTED, "plan has a cold block that is not a contiguous tile of x");
-    int device = 0;
+        if (!(plan.chunk_flags[c] & (kChunkHot | kChunkContig))) sparse_ok = false;
+    int device = 0, smem_optin = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&dev.sm_count, cudaDevAttrMultiProcessorCount, device));
+    SMX_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     int rc;
-    if ((rc = fast_kernel_prepare(dev))) return rc;
+    std::vector<int32_t> pairs(plan.tab_parent.size() * 2);
+    for (size_t i = 0; i < plan.tab_parent.size(); ++i) pairs[2 * i] = plan.tab_parent[i], pairs[2 * i + 1] = plan.tab_hot[i];
+    if ((rc = upload(plan.eta, &dev.eta, dev.bytes))) return rc;
+    if ((rc = upload(pairs, &dev.tab_pairs, dev.bytes, 2))) return rc;
+    if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
+    if ((rc = upload(plan.hot_pos, &dev.hot_pos, dev.bytes))) return rc;
+    if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
+    if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
+    if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
+    if (plan.has_dense && dense_kernel_fits(plan.n_tab, smem_optin)) {
+        dev.dense_k4 = plan.dense_k4;
+        if ((rc = upload(plan.dense_meta, &dev.dense_meta, dev.bytes, 2))) return rc;
+        if ((rc = upload(plan.dense_eta0, &dev.dense_eta0, dev.bytes))) return rc;
+        if ((rc = upload(plan.dense_coef, &dev.dense_coef, dev.bytes))) return rc;
+        dev.has_dense = true;
+    }
+    if (!sparse_ok) {
+        if (!dev.has_dense)
+            return fail(SMX_ERR_UNSUPPORTED, plan.has_sparse ? "plan has a cold block that is not a contiguous tile of x"
+                                                             : "value table does not fit in shared memory");
+        return SMX_OK;
+    }
+    if ((rc = fast_kernel_prepare(dev))) return dev.has_dense ? SMX_OK : rc;
 
     std::vector<double> packed;
     std::vector<int32_t> kstep_off;
@@ -109,29 +133,21 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         }
         for (int w = nw; w <= kMaxWarps; ++w) dev.warp_off[w] = (int32_t)pos;
     }
-    std::vector<int32_t> pairs(plan.tab_parent.size() * 2);
-    for (size_t i = 0; i < plan.tab_parent.size(); ++i) pairs[2 * i] = plan.tab_parent[i], pairs[2 * i + 1] = plan.tab_hot[i];
-    if ((rc = upload(plan.eta, &dev.eta, dev.bytes))) return rc;
-    if ((rc = upload(pairs, &dev.tab_pairs, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
-    if ((rc = upload(plan.hot_off, &dev.hot_off, dev.bytes))) return rc;
-    if ((rc = upload(plan.hot_pos, &dev.hot_pos, dev.bytes))) return rc;
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
     if ((rc = upload(meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
     if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
-    if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
     dev.n_sets = plan.n_sets;
     dev.n_gd = (int32_t)plan.grad_dims.size();
     dev.grad_ok = plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) && (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0);
     if ((rc = upload(plan.grad_dims, &dev.grad_dims, dev.bytes))) return rc;
-    if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
-    if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
+    dev.has_sparse = true;
     return SMX_OK;
 }
 
 void fast_free(FastDevice& d) {
     void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0,
-                    d.grad_dims, d.nan_off, d.nan_nodes};
+                    d.grad_dims, d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -202,12 +218,38 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
 
 int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
     if (N == 0) return SMX_OK;
+    if (!d.has_sparse) return fail(SMX_ERR_UNSUPPORTED, "plan has no block-sparse form");
     return run_fast(d, x, N, ldx, y, 0, st);
+}
+
+int dense_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
+    if (N == 0) return SMX_OK;
+    if (!d.has_dense) return fail(SMX_ERR_UNSUPPORTED, "plan has no dense form");
+    DenseArgs a;
+    a.eta = d.eta;
+    a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
+    a.hot_off = d.hot_off;
+    a.hot_pos = d.hot_pos;
+    a.meta = reinterpret_cast<const int2*>(d.dense_meta);
+    a.eta0 = d.dense_eta0;
+    a.coef = d.dense_coef;
+    a.c0 = d.c0;
+    a.N = N;
+    a.ldx = ldx;
+    a.d_out = d.d_out;
+    a.k4 = d.dense_k4;
+    a.nblk = (int)((d.d_out + 7) / 8);
+    a.n_tab = d.n_tab;
+    a.n_hot_rows = d.n_hot_rows;
+    a.n_levels = d.n_levels;
+    a.hot_dims = d.hot_dims;
+    for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
+    return dense_kernel_launch(a, x, y, st);
 }
 
 int fast_gradient(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st) {
     if (N == 0) return SMX_OK;
-    if (!d.grad_ok) return fail(SMX_ERR_UNSUPPORTED, "plan has no derivative sets");
+    if (!d.has_sparse || !d.grad_ok) return fail(SMX_ERR_UNSUPPORTED, "plan has no derivative sets");
     // dimensions without any entry keep derivative zero; everything else is written by the kernel
     SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * d.d_out * d.d_in, st));
     int rc = run_fast(d, x, N, ldx, J, 1, st);

@@ -92,56 +92,163 @@ std::vector<double> leja_order(const double* pts, int n) {
     return out;
 }
 
+// One summand (multi-index nu with zeta != 0), wherever its tables live: in the reference's padded per-group layout or
+// in the compact node-indexed form of smx_create_compact.
 struct Summand {
-    int group;
-    int64_t s;
-    int n;
-    int64_t zeta;
-    int64_t mu_off;  // offset into mu_terms
-    int64_t count;   // prod (deg+1)
+    int n = 0;
+    int64_t zeta = 0;
+    int64_t mu_off = 0;  // offset into mu_terms
+    int64_t count = 1;   // prod (deg+1)
+    const int64_t* dims = nullptr;
+    const int64_t* degs = nullptr;
+    const double* nodes[kMaxLevels] = {nullptr};  // per slot: its deg+1 nodes
+    const double* quad[kMaxLevels] = {nullptr};   // per slot: its quadrature weights (optional)
+    // values: either the summand's block of the padded F (element strides per axis, stride between outputs) ..
+    const double* F = nullptr;
+    int64_t fstride[kMaxLevels] = {0};
+    int64_t ostride = 0;
+    // .. or, per entry of the exact-shape tensor (C order over the slots), a row of the (n_values, d_out) value table
+    const int64_t* vidx = nullptr;
+    const double* values = nullptr;
+    int64_t vstride = 0;
 };
+
+std::string compact_summands(int64_t d_out, const CompactView& cv, std::vector<Summand>& summands) {
+    if (cv.n_summands < 0 || (cv.n_summands > 0 && (!cv.n_active || !cv.slot_off || !cv.dims || !cv.degs || !cv.node_off ||
+                                                    !cv.node_pool || !cv.zetas || !cv.val_off || !cv.val_index || !cv.values)))
+        return "compact descriptor has null arrays";
+    for (int64_t s = 0; s < cv.n_summands; ++s) {
+        Summand sm;
+        sm.n = cv.n_active[s];
+        if (sm.n <= 0 || sm.n > kMaxLevels) return "summand with unsupported number of active dimensions";
+        if (cv.slot_off[s + 1] - cv.slot_off[s] != sm.n) return "slot_off does not match n_active";
+        sm.zeta = cv.zetas[s];
+        sm.dims = cv.dims + cv.slot_off[s];
+        sm.degs = cv.degs + cv.slot_off[s];
+        int64_t count = 1;
+        for (int j = 0; j < sm.n; ++j) {
+            sm.nodes[j] = cv.node_pool + cv.node_off[cv.slot_off[s] + j];
+            sm.quad[j] = cv.quad_pool ? cv.quad_pool + cv.node_off[cv.slot_off[s] + j] : nullptr;
+            if (sm.degs[j] < 1) return "sorted_degs entry out of range";
+            count *= (sm.degs[j] + 1);
+        }
+        if (cv.val_off[s + 1] - cv.val_off[s] != count) return "val_off does not match the summand's shape";
+        sm.vidx = cv.val_index + cv.val_off[s];
+        for (int64_t i = 0; i < count; ++i)
+            if (sm.vidx[i] < 0 || sm.vidx[i] >= cv.n_values) return "val_index entry out of range";
+        sm.values = cv.values;
+        sm.vstride = d_out;
+        summands.push_back(sm);
+    }
+    return "";
+}
+
 
 }  // namespace
 
+static std::string build_from_summands(int64_t d_in, int64_t d_out, const double* offset, std::vector<Summand>& summands,
+                                       int64_t w_pad, FastPlan& plan, const PlanOptions& opt);
+
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
-                            FastPlan& plan, bool with_gradient) {
+                            FastPlan& plan, const PlanOptions& opt) {
+    std::vector<Summand> summands;
+    int64_t w_pad = 0;
+    for (const GroupView& G : groups) {
+        if (G.n <= 0 || G.n > kMaxLevels) return "group with unsupported number of active dimensions";
+        if ((int)G.tau.size() != G.n) return "tau has wrong length";
+        if (!G.F || !G.nodes || !G.dims || !G.degs || !G.zetas) return "group descriptor has null arrays";
+        const int64_t tw = G.tw(), fsize = G.fsize();
+        w_pad += G.nn * fsize;
+        for (int64_t s = 0; s < G.nn; ++s) {
+            Summand sm;
+            sm.n = G.n;
+            sm.zeta = G.zetas[s];
+            sm.dims = G.dims + s * G.n;
+            sm.degs = G.degs + s * G.n;
+            for (int j = G.n - 1; j >= 0; --j) {
+                if (sm.degs[j] > G.tau[j]) return "sorted_degs entry out of range";
+                sm.nodes[j] = G.nodes + (s * G.n + j) * tw;
+                sm.quad[j] = G.quad ? G.quad + (s * G.n + j) * tw : nullptr;
+                sm.fstride[j] = (j == G.n - 1) ? 1 : sm.fstride[j + 1] * (G.tau[j + 1] + 1);
+            }
+            sm.F = G.F + s * d_out * fsize;
+            sm.ostride = fsize;
+            summands.push_back(sm);
+        }
+    }
+    return build_from_summands(d_in, d_out, offset, summands, w_pad, plan, opt);
+}
+
+std::string build_fast_plan_compact(int64_t d_in, int64_t d_out, const double* offset, const CompactView& cv, FastPlan& plan,
+                                    const PlanOptions& opt) {
+    std::vector<Summand> summands;
+    const std::string err = compact_summands(d_out, cv, summands);
+    if (!err.empty()) return err;
+    return build_from_summands(d_in, d_out, offset, summands, 0, plan, opt);
+}
+
+// Smolyak quadrature of the summands in long double:  Q[o] = offset[o] + sum_s zeta_s sum_mu value(mu)[o] prod_j quad_j[mu_j]
+std::string integrate_compact(int64_t d_out, const double* offset, const CompactView& cv, std::vector<double>& Q) {
+    std::vector<Summand> summands;
+    const std::string err = compact_summands(d_out, cv, summands);
+    if (!err.empty()) return err;
+    std::vector<ld> acc((size_t)d_out, 0.0L);
+    for (int64_t o = 0; o < d_out; ++o) acc[o] = offset ? (ld)offset[o] : 0.0L;
+    for (const Summand& sm : summands) {
+        int mu[kMaxLevels] = {0};
+        int64_t count = 1;
+        for (int j = 0; j < sm.n; ++j) {
+            if (!sm.quad[j]) return "no quadrature weights in the compact descriptor";
+            count *= sm.degs[j] + 1;
+        }
+        for (int64_t idx = 0; idx < count; ++idx) {
+            ld w = (ld)sm.zeta;
+            for (int j = 0; j < sm.n; ++j) w *= (ld)sm.quad[j][mu[j]];
+            const double* v = sm.values + sm.vidx[idx] * sm.vstride;
+            for (int64_t o = 0; o < d_out; ++o) acc[o] += w * (ld)v[o];
+            for (int j = sm.n - 1; j >= 0; --j) {
+                if (++mu[j] <= sm.degs[j]) break;
+                mu[j] = 0;
+            }
+        }
+    }
+    Q.resize((size_t)d_out);
+    for (int64_t o = 0; o < d_out; ++o) Q[o] = (double)acc[o];
+    return "";
+}
+
+static std::string build_from_summands(int64_t d_in, int64_t d_out, const double* offset, std::vector<Summand>& summands,
+                                       int64_t w_pad, FastPlan& plan, const PlanOptions& opt) {
+    const bool with_gradient = opt.gradient && opt.sparse;
     plan = FastPlan();
     plan.d_in = d_in;
     plan.d_out = d_out;
+    plan.w_pad = w_pad;
     if (d_in <= 0 || d_out <= 0) return "d_in and d_out must be positive";
 
     // ---- 1. unique (dim, deg) pairs, per-dimension maximal degree ------------------------------------------
     std::map<std::pair<int, int>, int> pair_id;
     std::vector<PairInfo> pairs;
     std::vector<int> maxdeg((size_t)d_in, 0);
-    std::vector<Summand> summands;
     int64_t total_mu = 0;
-    for (size_t g = 0; g < groups.size(); ++g) {
-        const GroupView& G = groups[g];
-        if (G.n <= 0 || G.n > kMaxLevels) return "group with unsupported number of active dimensions";
-        if ((int)G.tau.size() != G.n) return "tau has wrong length";
-        if (!G.F || !G.nodes || !G.dims || !G.degs || !G.zetas) return "group descriptor has null arrays";
-        const int64_t tw = G.tw();
-        plan.w_pad += G.nn * G.fsize();
-        for (int64_t s = 0; s < G.nn; ++s) {
-            Summand sm{(int)g, s, G.n, G.zetas[s], total_mu, 1};
-            for (int j = 0; j < G.n; ++j) {
-                const int64_t dim = G.dims[s * G.n + j], deg = G.degs[s * G.n + j];
-                if (dim < 0 || dim >= d_in) return "sorted_dims entry out of range";
-                if (deg < 1 || deg > G.tau[j] || deg >= kCode) return "sorted_degs entry out of range";
-                for (int i = 0; i < j; ++i)
-                    if (G.dims[s * G.n + i] == dim) return "duplicate dimension inside one summand";
-                auto key = std::make_pair((int)dim, (int)deg);
-                if (!pair_id.count(key)) {
-                    pair_id[key] = (int)pairs.size();
-                    pairs.push_back({(int)dim, (int)deg, G.nodes + (s * G.n + j) * tw, {}});
-                }
-                maxdeg[dim] = std::max(maxdeg[dim], (int)deg);
-                sm.count *= (deg + 1);
+    for (Summand& sm : summands) {
+        sm.mu_off = total_mu;
+        sm.count = 1;
+        for (int j = 0; j < sm.n; ++j) {
+            const int64_t dim = sm.dims[j], deg = sm.degs[j];
+            if (dim < 0 || dim >= d_in) return "sorted_dims entry out of range";
+            if (deg < 1 || deg >= kCode) return "sorted_degs entry out of range";
+            for (int i = 0; i < j; ++i)
+                if (sm.dims[i] == dim) return "duplicate dimension inside one summand";
+            auto key = std::make_pair((int)dim, (int)deg);
+            if (!pair_id.count(key)) {
+                pair_id[key] = (int)pairs.size();
+                pairs.push_back({(int)dim, (int)deg, sm.nodes[j], {}});
             }
-            total_mu += sm.count;
-            summands.push_back(sm);
+            maxdeg[dim] = std::max(maxdeg[dim], (int)deg);
+            sm.count *= (deg + 1);
         }
+        total_mu += sm.count;
     }
     plan.n_summands = (int64_t)summands.size();
     plan.w_raw = total_mu;
@@ -193,12 +300,11 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         Key key;
         std::vector<std::pair<int64_t, int>> act;
         for (const Summand& sm : summands) {
-            const GroupView& G = groups[sm.group];
             int mu[kMaxLevels] = {0};
             for (int64_t idx = 0; idx < sm.count; ++idx) {
                 act.clear();
                 for (int j = 0; j < sm.n; ++j)
-                    if (mu[j] > 0) act.push_back({G.dims[sm.s * sm.n + j], mu[j]});
+                    if (mu[j] > 0) act.push_back({sm.dims[j], mu[j]});
                 std::sort(act.begin(), act.end());
                 key.clear();
                 for (auto& a : act) key.push_back(a.first * kCode + a.second);
@@ -213,7 +319,7 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
                 }
                 mu_terms[(size_t)(sm.mu_off + idx)] = id;
                 for (int j = sm.n - 1; j >= 0; --j) {  // odometer, last axis fastest (C order of F)
-                    if (++mu[j] <= G.degs[sm.s * sm.n + j]) break;
+                    if (++mu[j] <= sm.degs[j]) break;
                     mu[j] = 0;
                 }
             }
@@ -234,24 +340,25 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             for (int64_t ch = c_begin; ch < c_end; ++ch) {
                 const int64_t o0 = ch * och_max, och = std::min(och_max, d_out - o0);
                 for (const Summand& sm : summands) {
-                    const GroupView& G = groups[sm.group];
                     const int n = sm.n;
-                    const int64_t fsize = G.fsize();
                     int m[kMaxLevels], pid[kMaxLevels];
-                    int64_t fstride[kMaxLevels], mstride[kMaxLevels];
+                    int64_t mstride[kMaxLevels];
                     for (int j = n - 1; j >= 0; --j) {
-                        m[j] = (int)G.degs[sm.s * n + j] + 1;
-                        pid[j] = pair_id[{(int)G.dims[sm.s * n + j], m[j] - 1}];
-                        fstride[j] = (j == n - 1) ? 1 : fstride[j + 1] * (G.tau[j + 1] + 1);
+                        m[j] = (int)sm.degs[j] + 1;
+                        pid[j] = pair_id.at({(int)sm.dims[j], m[j] - 1});
                         mstride[j] = (j == n - 1) ? 1 : mstride[j + 1] * m[j + 1];
                     }
-                    const double* Fs = G.F + sm.s * d_out * fsize;
                     Gt.resize((size_t)sm.count * och);
                     int mu[kMaxLevels] = {0};
                     for (int64_t idx = 0; idx < sm.count; ++idx) {
-                        int64_t foff = 0;
-                        for (int j = 0; j < n; ++j) foff += mu[j] * fstride[j];
-                        for (int64_t oo = 0; oo < och; ++oo) Gt[(size_t)(idx * och + oo)] = (ld)Fs[(o0 + oo) * fsize + foff];
+                        if (sm.vidx) {
+                            const double* v = sm.values + sm.vidx[idx] * sm.vstride + o0;
+                            for (int64_t oo = 0; oo < och; ++oo) Gt[(size_t)(idx * och + oo)] = (ld)v[oo];
+                        } else {
+                            int64_t foff = 0;
+                            for (int j = 0; j < n; ++j) foff += mu[j] * sm.fstride[j];
+                            for (int64_t oo = 0; oo < och; ++oo) Gt[(size_t)(idx * och + oo)] = (ld)sm.F[(o0 + oo) * sm.ostride + foff];
+                        }
                         for (int j = n - 1; j >= 0; --j) {
                             if (++mu[j] < m[j]) break;
                             mu[j] = 0;
@@ -463,6 +570,21 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     if (maxlevel < 2) plan.level_off.assign(plan.level_off.size(), next);
     plan.n_tab = next;
 
+    // ---- (last step, shared by both forms) nodes per dimension: the reference's gradient is NaN where a coordinate sits
+    // on one of them
+    auto finish_nodes = [&]() -> std::string {
+        std::vector<std::vector<double>> per_dim((size_t)d_in);
+        for (const PairInfo& pr : pairs) per_dim[pr.dim].insert(per_dim[pr.dim].end(), pr.nodes, pr.nodes + pr.deg + 1);
+        plan.nan_off.assign((size_t)d_in + 1, 0);
+        for (int64_t d = 0; d < d_in; ++d) {
+            std::sort(per_dim[d].begin(), per_dim[d].end());
+            per_dim[d].erase(std::unique(per_dim[d].begin(), per_dim[d].end()), per_dim[d].end());
+            plan.nan_nodes.insert(plan.nan_nodes.end(), per_dim[d].begin(), per_dim[d].end());
+            plan.nan_off[d + 1] = (int32_t)plan.nan_nodes.size();
+        }
+        return "";
+    };
+
     // ---- 9. block-sparse coefficient matrix and work items ------------------------------------------------------
     struct Nz {
         int32_t block, row, lane, term;
@@ -479,6 +601,34 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
         if (a.row != b.row) return a.row < b.row;
         return a.lane < b.lane;
     });
+    // ---- 9a. dense form ------------------------------------------------------------------------------------------------
+    if (opt.dense) {
+        const int64_t K = (int64_t)nz.size();
+        plan.dense_k4 = (int32_t)((K + 3) / 4);
+        plan.dense_meta.assign((size_t)plan.dense_k4 * 8, 0);  // padding terms: ones row * ones row, zero coefficients
+        plan.dense_eta0.assign((size_t)d_in, 0.0);
+        for (int64_t d = 0; d < d_in; ++d)
+            if (maxdeg[d] > 0) plan.dense_eta0[d] = plan.eta[eta_off[d]];
+        const int64_t nblk = (d_out + 7) / 8;
+        plan.dense_coef.assign((size_t)nblk * plan.dense_k4 * 32, 0.0);
+        for (int64_t i = 0; i < K; ++i) {
+            const int32_t e = nz[i].block * kBlockWidth + nz[i].lane;
+            plan.dense_meta[2 * i] = nz[i].row;
+            plan.dense_meta[2 * i + 1] = plan.ent_tab[e] > 0 ? plan.ent_tab[e] : -1 - plan.ent_dim[e];
+            const int64_t k4 = i >> 2, tig = i & 3;
+            const ld* src = &C[(size_t)nz[i].term * d_out];
+            for (int64_t o = 0; o < d_out; ++o)
+                plan.dense_coef[(size_t)(((o >> 3) * plan.dense_k4 + k4) * 32 + 4 * (o & 7) + tig)] = (double)src[o];
+        }
+        plan.has_dense = true;
+    }
+    if (!opt.sparse) {
+        plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
+        for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
+        if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
+        return finish_nodes();
+    }
+    plan.has_sparse = true;
     auto block_flags = [&](int32_t b) {
         int flags = kChunkHot | kChunkContig;
         const int32_t e0 = b * kBlockWidth;
@@ -598,19 +748,7 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
     for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
     if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
 
-    // ---- 11. nodes per dimension (the reference's gradient is NaN where a coordinate sits on one of them) -------------
-    {
-        std::vector<std::vector<double>> per_dim((size_t)d_in);
-        for (const PairInfo& pr : pairs) per_dim[pr.dim].insert(per_dim[pr.dim].end(), pr.nodes, pr.nodes + pr.deg + 1);
-        plan.nan_off.assign((size_t)d_in + 1, 0);
-        for (int64_t d = 0; d < d_in; ++d) {
-            std::sort(per_dim[d].begin(), per_dim[d].end());
-            per_dim[d].erase(std::unique(per_dim[d].begin(), per_dim[d].end()), per_dim[d].end());
-            plan.nan_nodes.insert(plan.nan_nodes.end(), per_dim[d].begin(), per_dim[d].end());
-            plan.nan_off[d + 1] = (int32_t)plan.nan_nodes.size();
-        }
-    }
-    return "";
+    return finish_nodes();
 }
 
 void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y) {
@@ -642,6 +780,34 @@ void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ld
                         acc[o] = std::fma(plan.coef[((size_t)i * plan.n_sets + o) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc[o]);
                 for (int64_t o = 0; o < d_out; ++o) yp[o] = std::fma(v, acc[o], yp[o]);
             }
+        }
+    }
+}
+
+void eval_plan_dense_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y) {
+    const int64_t d_out = plan.d_out;
+    std::vector<double> tab((size_t)plan.n_tab, 1.0);
+    auto pi = [&](const double* xp, int32_t e) {
+        double v = 1.0;
+        for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
+        return v;
+    };
+    for (int64_t p = 0; p < N; ++p) {
+        const double* xp = x + p * ldx;
+        tab[0] = 1.0;
+        for (size_t e = 0; e < plan.ent_dim.size(); ++e)
+            if (plan.ent_tab[e] > 0) tab[plan.ent_tab[e]] = pi(xp, (int32_t)e);
+        for (int32_t t = 1 + plan.n_hot_rows; t < plan.n_tab; ++t)
+            tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot_rows]] * tab[plan.tab_hot[t - 1 - plan.n_hot_rows]];
+        double* yp = y + p * d_out;
+        for (int64_t o = 0; o < d_out; ++o) {
+            double acc = 0.0;
+            for (int64_t i = 0; i < 4 * (int64_t)plan.dense_k4; ++i) {
+                const int32_t ia = plan.dense_meta[2 * i], ib = plan.dense_meta[2 * i + 1];
+                const double phi = tab[ia] * (ib >= 0 ? tab[ib] : xp[-1 - ib] - plan.dense_eta0[-1 - ib]);
+                acc = std::fma(phi, plan.dense_coef[(size_t)(((o >> 3) * plan.dense_k4 + (i >> 2)) * 32 + 4 * (o & 7) + (i & 3))], acc);
+            }
+            yp[o] = plan.c0[o] + acc;
         }
     }
 }
@@ -705,7 +871,15 @@ struct smxh_group {
 static thread_local std::string g_plan_error;
 const char* smxh_plan_error() { return g_plan_error.c_str(); }
 
-void* smxh_plan_build(int64_t d_in, int64_t d_out, const double* offset, int32_t n_groups, const smxh_group* groups) {
+// option bits: 1 = derivative sets, 2 = block-sparse form, 4 = dense form
+static smx::PlanOptions plan_options(int32_t bits) {
+    smx::PlanOptions o;
+    o.gradient = bits & 1, o.sparse = bits & 2, o.dense = bits & 4;
+    return o;
+}
+
+void* smxh_plan_build_opt(int64_t d_in, int64_t d_out, const double* offset, int32_t n_groups, const smxh_group* groups,
+                          int32_t option_bits) {
     std::vector<smx::GroupView> gv;
     for (int32_t g = 0; g < n_groups; ++g) {
         smx::GroupView v;
@@ -722,12 +896,64 @@ void* smxh_plan_build(int64_t d_in, int64_t d_out, const double* offset, int32_t
         gv.push_back(v);
     }
     auto* plan = new smx::FastPlan();
-    g_plan_error = smx::build_fast_plan(d_in, d_out, offset, gv, *plan);
+    g_plan_error = smx::build_fast_plan(d_in, d_out, offset, gv, *plan, plan_options(option_bits));
     if (!g_plan_error.empty()) {
         delete plan;
         return nullptr;
     }
     return plan;
+}
+void* smxh_plan_build(int64_t d_in, int64_t d_out, const double* offset, int32_t n_groups, const smxh_group* groups) {
+    return smxh_plan_build_opt(d_in, d_out, offset, n_groups, groups, 3);
+}
+// Same field order as smx_compact_desc (include/smolyax_b200.h) and smx::CompactView.
+struct smxh_compact {
+    int64_t n_summands;
+    const int32_t* n_active;
+    const int64_t* slot_off;
+    const int64_t* dims;
+    const int64_t* degs;
+    const int64_t* node_off;
+    const double* node_pool;
+    const double* quad_pool;
+    const int64_t* zetas;
+    const int64_t* val_off;
+    const int64_t* val_index;
+    const double* values;
+    int64_t n_values;
+};
+static smx::CompactView compact_view(const smxh_compact* c) {
+    smx::CompactView v;
+    v.n_summands = c->n_summands;
+    v.n_active = c->n_active;
+    v.slot_off = c->slot_off;
+    v.dims = c->dims;
+    v.degs = c->degs;
+    v.node_off = c->node_off;
+    v.node_pool = c->node_pool;
+    v.quad_pool = c->quad_pool;
+    v.zetas = c->zetas;
+    v.val_off = c->val_off;
+    v.val_index = c->val_index;
+    v.values = c->values;
+    v.n_values = c->n_values;
+    return v;
+}
+void* smxh_plan_build_compact(int64_t d_in, int64_t d_out, const double* offset, const smxh_compact* desc, int32_t option_bits) {
+    auto* plan = new smx::FastPlan();
+    g_plan_error = smx::build_fast_plan_compact(d_in, d_out, offset, compact_view(desc), *plan, plan_options(option_bits));
+    if (!g_plan_error.empty()) {
+        delete plan;
+        return nullptr;
+    }
+    return plan;
+}
+int smxh_integrate_compact(int64_t d_out, const double* offset, const smxh_compact* desc, double* Q) {
+    std::vector<double> q;
+    g_plan_error = smx::integrate_compact(d_out, offset, compact_view(desc), q);
+    if (!g_plan_error.empty()) return 1;
+    std::memcpy(Q, q.data(), sizeof(double) * (size_t)d_out);
+    return 0;
 }
 void smxh_plan_free(void* p) { delete static_cast<smx::FastPlan*>(p); }
 // stats: [n_terms, n_entries, n_rows, n_hot, n_chunks, padded_fma, n_levels, nested, n_summands, w_raw, w_pad]
@@ -741,6 +967,9 @@ void smxh_plan_stats(void* p, int64_t* out) {
 // Verification aid, CPU tests only (see smx_plan.h).
 void smxh_plan_eval_host(void* p, const double* x, int64_t N, int64_t ldx, double* y) {
     smx::eval_plan_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, y);
+}
+void smxh_plan_eval_dense_host(void* p, const double* x, int64_t N, int64_t ldx, double* y) {
+    smx::eval_plan_dense_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, y);
 }
 void smxh_plan_gradient_host(void* p, const double* x, int64_t N, int64_t ldx, double* J) {
     smx::eval_plan_gradient_host(*static_cast<smx::FastPlan*>(p), x, N, ldx, J);

@@ -43,6 +43,24 @@ struct GroupView {
     }
 };
 
+// The same information in compact form (smx_create_compact): summands as CSR over their slots, values as rows of one
+// (n_values, d_out) table shared by all summands (nested rules: one row per sparse-grid node).
+struct CompactView {
+    int64_t n_summands = 0;
+    const int32_t* n_active = nullptr;   // (n_summands)
+    const int64_t* slot_off = nullptr;   // (n_summands + 1)
+    const int64_t* dims = nullptr;       // (slots)
+    const int64_t* degs = nullptr;       // (slots)
+    const int64_t* node_off = nullptr;   // (slots) offset of the slot's deg+1 nodes in node_pool (and weights in quad_pool)
+    const double* node_pool = nullptr;
+    const double* quad_pool = nullptr;   // optional
+    const int64_t* zetas = nullptr;      // (n_summands)
+    const int64_t* val_off = nullptr;    // (n_summands + 1)
+    const int64_t* val_index = nullptr;  // per entry of the exact-shape value tensor (C order over the slots): row of `values`
+    const double* values = nullptr;      // (n_values, d_out)
+    int64_t n_values = 0;
+};
+
 constexpr int kBlockWidth = 16;    // entries per block: 4 lane-groups x 4 entries per lane
 constexpr int kChunkRows = 16;     // rows per work item
 constexpr int kMaxLevels = 16;
@@ -112,6 +130,24 @@ struct FastPlan {
     std::vector<double> c0;              // (d_out) constant term, includes the offset
     int64_t padded_fma = 0;              // FMAs per point and output the kernel executes: 32 per non-empty (k-step, half block)
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
+    bool has_sparse = false;             // work items + coefficient sets above are filled
+
+    // Dense (GEMM-regime) form for large d_out:  y = c0 + Phi(x) C  with one column of Phi per term,
+    // Phi[p][t] = tab[hot part of t][p] * pi_{leading entry of t}(x_p)  and  C (terms x d_out).  Terms are ordered hot
+    // entries first (by block, row), then by column of x; padded with zero rows to whole k-steps of 4 terms.
+    bool has_dense = false;
+    int32_t dense_k4 = 0;                // k-steps
+    std::vector<int32_t> dense_meta;     // 2 ints per term: table row of the hot part; table row of the leading entry
+                                         // (hot) or  -1 - column of x  (cold: pi = x - eta0[column])
+    std::vector<double> dense_eta0;      // (d_in) first centre of every dimension
+    std::vector<double> dense_coef;      // [ceil(d_out / 8)][dense_k4][32]: DMMA B fragments, lane = 4 * gid + tig holds
+                                         // C[4 * k4 + tig][8 * jb + gid]
+};
+
+struct PlanOptions {
+    bool gradient = true;   // derivative coefficient sets (sparse form only)
+    bool sparse = true;     // block-sparse work items (K1; values and gradients)
+    bool dense = false;     // dense term matrix (K2; values, large d_out)
 };
 
 // value-table row (minus one) of hot entry h
@@ -122,11 +158,18 @@ inline int32_t hot_row(int32_t h) { return (h & ~15) | ((h & 3) << 2) | ((h >> 2
 
 // Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
-                            FastPlan& plan, bool with_gradient = true);
+                            FastPlan& plan, const PlanOptions& opt = PlanOptions());
+
+std::string build_fast_plan_compact(int64_t d_in, int64_t d_out, const double* offset, const CompactView& cv, FastPlan& plan,
+                                    const PlanOptions& opt = PlanOptions());
+// Smolyak quadrature of a compact descriptor on the host, in long double (the integral does not depend on x).
+std::string integrate_compact(int64_t d_out, const double* offset, const CompactView& cv, std::vector<double>& Q);
 
 // Verification aid for the CPU-only test-suite: evaluates the plan on the host in fp64 in the same order as
 // the kernel.  NOT a product path — nothing in smolyax_b200/ calls it; see tests/test_plan.py.
 void eval_plan_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y);
+// same for the dense form (mirrors the arithmetic of the GEMM-regime kernel)
+void eval_plan_dense_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* y);
 // same for the gradient sets: J (N, d_out, d_in), finite at nodes
 void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* J);
 

@@ -61,7 +61,8 @@ class SmolyakBarycentricInterpolator:
     # ------------------------------------------------------------------ construction (interpolation.py:51-113)
     def __init__(self, node_gen=None, k: Sequence[float] = None, d_out: int = None, t: float = None,
                  f: Callable = None, *, n_inputs: int = None, memory_limit: float = 4.0, method: str = "auto",
-                 device: int = None, batched_f: bool = False, nan_at_nodes: bool = True) -> None:
+                 device: int = None, batched_f: bool = False, nan_at_nodes: bool = True, layout: str = "auto",
+                 dense: bool = None) -> None:
         r"""
         Parameters (all accepted as keywords, as in the reference)
         ----------
@@ -89,9 +90,21 @@ class SmolyakBarycentricInterpolator:
         nan_at_nodes : bool
             ``gradient`` returns ``NaN`` in a dimension whose coordinate sits exactly on an interpolation node, as the
             reference does (default).  ``False`` returns the true, finite derivative there (fast path only).
+        layout : {"auto", "reference", "compact"}
+            "reference": ``set_f`` assembles the reference's zero-padded per-group tables (``reference_layout()``) and
+            hands them to ``smx_create``.  "compact": it hands over the exact-shape, node-indexed form instead
+            (``smx_create_compact``; one row of function values per interpolation node for nested rules) — the only
+            form that fits in memory when ``d_out`` is in the thousands; ``reference_layout()`` and
+            ``method="barycentric"`` are then unavailable.  "auto": compact when the padded value tensors would
+            exceed 1 GiB.
+        dense : bool, optional
+            Force (True) or forbid (False) the GEMM-regime form of the value path; default: the library decides
+            (``d_out >= 32``).
         """
         assert node_gen is not None and k is not None and d_out is not None and t is not None
         assert method in ("auto", "barycentric")
+        assert layout in ("auto", "reference", "compact")
+        assert not (layout == "compact" and method == "barycentric"), "the per-summand kernels need the reference layout"
         self._d_in = len(k)
         self._d_out = int(d_out)
         self._node_gen = node_gen
@@ -104,6 +117,8 @@ class SmolyakBarycentricInterpolator:
         self._nan_at_nodes = nan_at_nodes
         self._memory_limit = memory_limit
         self._n_inputs = n_inputs
+        self._layout_mode = layout
+        self._dense = dense
 
         self._layout = None
         self._handle = None
@@ -125,19 +140,130 @@ class SmolyakBarycentricInterpolator:
         """Evaluate (or reuse from ``f_evals``) the target function at the interpolation nodes and build the device
         tables.  Returns the updated dictionary of evaluations: flat ``{mu_tuple: value}`` for nested rules,
         ``{nu: {mu_tuple: value}}`` otherwise (reference interpolation.py:119,155-163,208-228)."""
-        layout, f_evals = self._assemble(f, {} if f_evals is None else f_evals)
+        f_evals = {} if f_evals is None else f_evals
+        mode = self._layout_mode
+        if mode == "auto":
+            mode = "compact" if self._method != "barycentric" and self._padded_bytes() > (1 << 30) else "reference"
+        layout, f_evals = (self._assemble_compact if mode == "compact" else self._assemble)(f, f_evals)
         self.set_layout(layout)
         return f_evals
+
+    def _padded_bytes(self) -> int:
+        """Size of the reference's zero-padded value tensors ``F_n`` (interpolation.py:203) for this index set."""
+        offsets, _, degs_all, _ = indices.nonzero_arrays(self._k, self._t)
+        lengths = np.diff(offsets)
+        total = 0
+        for n in set(lengths.tolist()) - {0}:
+            sel = np.flatnonzero(lengths == n)
+            degs = -np.sort(-degs_all[offsets[sel][:, None] + np.arange(n)[None, :]].astype(np.int64), axis=1)
+            total += len(sel) * int(np.prod(degs.max(axis=0) + 1))
+        return 8 * total * self._d_out
 
     def set_layout(self, layout: dict) -> None:
         """Build the device tables from an already assembled reference layout (``reference_layout()`` of another
         instance, e.g. received through ``dist.broadcast_layout``) instead of evaluating ``f`` again."""
         self._layout = layout
         self._release()
-        flags = _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
-        flags |= 0 if self._nan_at_nodes else _lib.SMX_GRAD_FINITE_AT_NODES
+        flags = 0 if self._nan_at_nodes else _lib.SMX_GRAD_FINITE_AT_NODES
+        if self._dense is not None:
+            flags |= _lib.SMX_DENSE_PATH if self._dense else _lib.SMX_NO_DENSE_PATH
         with torch.cuda.device(self._device):
-            self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
+            if layout.get("compact"):
+                assert self._method != "barycentric", "the per-summand kernels need the reference layout"
+                self._handle = _lib.create_compact(layout, self._d_in, self._d_out, flags, self._device)
+            else:
+                flags |= _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
+                self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
+
+    def _assemble_compact(self, f: Callable, f_evals: dict):
+        """Host half of ``set_f`` without the reference's padding: summands in the order of the reference's walk, one
+        row of ``values`` per distinct function evaluation (smx_compact_desc in include/smolyax_b200.h).  Same
+        ``f_evals`` semantics and counters as :meth:`_assemble`."""
+        gen = self._node_gen
+        zero = np.array([g(0)[0] for g in gen])
+        offsets, dims_all, degs_all, zetas_all = indices.nonzero_arrays(self._k, self._t)
+        lengths = np.diff(offsets)
+        offset = np.zeros(self._d_out)
+
+        pool_at, pool_nodes, pool_quad, pool_len = {}, [], [], 0  # (generator, degree) -> offset into the pools
+        row_of, row_src, new_points = {}, [], []  # evaluation -> row of `values`; its value or None (pending)
+        n_active, slot_dims, slot_degs, slot_nodes, zetas, val_off, val_index = [], [], [], [], [], [0], []
+
+        for s in range(len(lengths)):
+            n = int(lengths[s])
+            dims_in = dims_all[offsets[s]:offsets[s + 1]].astype(np.int64)
+            degs_in = degs_all[offsets[s]:offsets[s + 1]].astype(np.int64)
+            nu = tuple(zip(dims_in.tolist(), degs_in.tolist()))
+            store = f_evals if self._is_nested else f_evals.setdefault(nu, {})
+            if n == 0:
+                if () not in store:
+                    store[()] = f(zero.copy())
+                    self._n_f_evals_new += 1
+                offset = np.asarray(int(zetas_all[s]) * np.asarray(store[()], dtype=float), dtype=float) * np.ones(self._d_out)
+                continue
+            order = np.argsort(-degs_in, kind="stable")  # interpolation.py:175; any order is valid for the compact form
+            sd, sg = dims_in[order], degs_in[order]
+            pts = []
+            for dim, deg in zip(sd.tolist(), sg.tolist()):
+                key = (id(gen[dim]), deg)
+                if key not in pool_at:
+                    p = np.asarray(gen[dim](deg), dtype=float)
+                    q = np.zeros(deg + 1)
+                    qw = np.asarray(gen[dim].get_quadrature_weights(deg), dtype=float)
+                    q[: len(qw)] = qw
+                    pool_at[key] = (pool_len, p)
+                    pool_nodes.append(p)
+                    pool_quad.append(q)
+                    pool_len += deg + 1
+                slot_nodes.append(pool_at[key][0])
+                pts.append(pool_at[key][1])
+            n_active.append(n)
+            slot_dims.extend(sd.tolist())
+            slot_degs.extend(sg.tolist())
+            zetas.append(int(zetas_all[s]))
+            by_dim = np.argsort(sd)
+            tag = None if self._is_nested else nu
+            for mu in it.product(*[range(int(v) + 1) for v in sg]):
+                key = tuple((int(sd[j]), mu[j]) for j in by_dim if mu[j] > 0)
+                row = row_of.get((tag, key))
+                if row is None:
+                    row = len(row_src)
+                    row_of[(tag, key)] = row
+                    if key in store:
+                        row_src.append(store[key])
+                    else:
+                        x = zero.copy()
+                        x[sd] = [pts[j][mu[j]] for j in range(n)]
+                        self._n_f_evals_new += 1
+                        if self._batched_f:
+                            row_src.append(None)
+                            new_points.append((row, store, key, x))
+                        else:
+                            store[key] = f(x)
+                            row_src.append(store[key])
+                val_index.append(row)
+            val_off.append(len(val_index))
+
+        values = np.empty((len(row_src), self._d_out))
+        if new_points:
+            vals = np.asarray(f(np.stack([p[3] for p in new_points])), dtype=float).reshape(len(new_points), -1)
+            for (row, store, key, _), v in zip(new_points, vals):
+                store[key] = v if self._d_out > 1 else (v[0] if v.size == 1 else v)
+                values[row] = v
+        for row, v in enumerate(row_src):
+            if v is not None:
+                values[row] = v
+        layout = {
+            "compact": True, "offset": offset, "n_active": np.asarray(n_active, dtype=np.int32),
+            "slot_off": np.concatenate([[0], np.cumsum(n_active, dtype=np.int64)]).astype(np.int64),
+            "dims": np.asarray(slot_dims, dtype=np.int64), "degs": np.asarray(slot_degs, dtype=np.int64),
+            "node_off": np.asarray(slot_nodes, dtype=np.int64),
+            "node_pool": np.concatenate(pool_nodes) if pool_nodes else np.zeros(1),
+            "quad_pool": np.concatenate(pool_quad) if pool_quad else np.zeros(1),
+            "zetas": np.asarray(zetas, dtype=np.int64), "val_off": np.asarray(val_off, dtype=np.int64),
+            "val_index": np.asarray(val_index, dtype=np.int64), "values": values,
+        }
+        return layout, f_evals
 
     def _assemble(self, f: Callable, f_evals: dict):
         """Host half of ``set_f``: the reference's per-group tables as NumPy arrays (no GPU needed)."""
@@ -241,6 +367,7 @@ class SmolyakBarycentricInterpolator:
         NumPy arrays keyed ``offset``, ``F_n``, ``nodes_n``, ``weights_n``, ``dims_n``, ``degs_n``, ``zetas_n``
         (+ ``quad_n``, the tables of interpolation.py:361-379)."""
         assert self._layout is not None, "The operator has not yet been set up for a target function via `set_f`."
+        assert not self._layout.get("compact"), "set_f used the compact layout; construct with layout='reference'"
         return self._layout
 
     def device_info(self) -> dict:

@@ -179,3 +179,85 @@ def test_barycentric_module_functions():
     assert np.allclose(b[:-1, :k], wt[0, 0, :k] / (xs[:-1, None] - nd[0, 0, :k])) and np.all(b[:, k:] == 0)
     assert np.array_equal(b[-1, :k], np.eye(k)[0]) and np.isnan(db[-1, 0]) and np.all(db[:, k:] == 0)
     assert np.allclose(db[:-1, :k], -wt[0, 0, :k] / (xs[:-1, None] - nd[0, 0, :k]) ** 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GEMM-regime form (K2) and the compact create entry
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_values_dense_path(case):
+    """smx_eval through the dense term matrix + FP64 tensor instruction (forced here; chosen by itself for d_out >= 32):
+    same bound against the reference as the block-sparse path, ragged batch sizes, bitwise repeatable."""
+    g, ip = _build(case, dense=True)
+    info = ip.device_info()
+    assert info["has_dense_path"] == 1 and info["dense_terms"] >= info["n_terms"] - 1
+    x = g["x"]
+    y = ip(x)
+    assert scaled_error(y, g["y_ref"], g["cond_abs"]) < 1e-12
+    y_ld = long_double(g, "y")
+    scale = np.max(np.abs(g["y_ref"]))
+    err_new = np.max(np.abs((y - y_ld).astype(float))) / scale
+    err_ref = np.max(np.abs((g["y_ref"] - y_ld).astype(float))) / scale
+    assert err_new <= max(err_ref, 5e-14)
+    _, sparse = _build(case, dense=False)
+    assert sparse.device_info()["has_dense_path"] == 0
+    assert scaled_error(y, sparse(x), g["cond_abs"]) < 1e-13
+    for n in (1, 31, 33, min(len(x), 77)):
+        assert np.array_equal(ip(x[:n]), y[:n])
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(ip(xd).cpu().numpy(), y)
+    # the gradient of a dense handle still comes from the block-sparse derivative sets
+    J_ref = g["J_ref"]
+    J = ip.gradient(x[: len(J_ref)])
+    assert np.array_equal(np.isnan(J), np.isnan(J_ref))
+
+
+@pytest.mark.parametrize("d_in,d_out,n_target,rule", [(10, 203, 300, "leja"), (6, 520, 120, "leja"), (8, 100, 200, "gh"),
+                                                       (12, 1031, 150, "leja")])
+def test_wide_outputs_against_oracle(d_in, d_out, n_target, rule):
+    """Vector-valued targets wide enough for every CTA shape of the dense kernel (1, 2 and 4 output blocks per warp,
+    partial last block, odd d_out): against the CPU oracle on the reference layout."""
+    from oracle import oracle
+    from smolyax_b200 import indices, nodes, workloads
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    w = workloads.Workload("wide", rule, d_in, d_out, n_target, 0)
+    # (f is called point by point: a batched matrix product may round differently depending on the row order)
+    ip = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(),
+                                        layout="reference")
+    assert ip.device_info()["has_dense_path"] == 1  # chosen without being asked for
+    x = w.points(301, seed=5)
+    y = ip(x)
+    y_orc = oracle.evaluate(ip.reference_layout(), x)
+    np.testing.assert_allclose(y, y_orc, rtol=0, atol=1e-12 * max(1.0, float(np.max(np.abs(y_orc)))) * 50)
+    sparse = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, dense=False,
+                                            layout="reference")
+    sparse.set_layout(ip.reference_layout())
+    np.testing.assert_allclose(y, sparse(x), rtol=0, atol=1e-13 * max(1.0, float(np.max(np.abs(y_orc)))) * 50)
+    # compact handle: same plan, hence the same bits; integral from the host quadrature
+    compact = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(),
+                                             layout="compact")
+    assert np.array_equal(compact(x), y)
+    np.testing.assert_allclose(compact.integral(), ip.integral(), rtol=1e-10, atol=1e-10)
+    with pytest.raises(AssertionError):
+        compact.reference_layout()
+
+
+@pytest.mark.parametrize("case", ["small_02", "small_07", "medium_03", "cfg1", "cfg3_dout16", "gh_d100"])
+def test_compact_layout_handle(case):
+    """smx_create_compact: values, gradient (same coefficient sets, same bits as the reference-layout handle) and the
+    integral (host quadrature in extended precision)."""
+    g, ref = _build(case, layout="reference")
+    _, ip = _build(case, layout="compact")
+    info, info_ref = ip.device_info(), ref.device_info()
+    assert info["has_groups"] == 0 and info["n_terms"] == info_ref["n_terms"] and info["w_raw"] == info_ref["w_raw"]
+    x = g["x"]
+    assert np.array_equal(ip(x), ref(x))
+    J_ref = g["J_ref"]
+    xs = x[: len(J_ref)]
+    J, J2 = ip.gradient(xs), ref.gradient(xs)
+    assert np.array_equal(np.isnan(J), np.isnan(J2)) and np.array_equal(np.nan_to_num(J), np.nan_to_num(J2))
+    Q_ld = long_double(g, "Q")
+    err_new = np.max(np.abs((ip.integral() - Q_ld).astype(float)))
+    err_ref = np.max(np.abs((g["Q_ref"] - Q_ld).astype(float)))
+    assert err_new <= max(err_ref, 1e-13 * max(1.0, float(np.max(np.abs(g["Q_ref"])))))

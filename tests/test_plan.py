@@ -18,6 +18,12 @@ class _Group(ctypes.Structure):
 _host = ctypes.CDLL(str(_build.build_host()))
 _host.smxh_plan_build.restype = ctypes.c_void_p
 _host.smxh_plan_build.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+_host.smxh_plan_build_opt.restype = ctypes.c_void_p
+_host.smxh_plan_build_opt.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32]
+_host.smxh_plan_build_compact.restype = ctypes.c_void_p
+_host.smxh_plan_build_compact.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+_host.smxh_integrate_compact.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+_host.smxh_plan_eval_dense_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
 _host.smxh_plan_error.restype = ctypes.c_char_p
 _host.smxh_plan_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 _host.smxh_plan_eval_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
@@ -26,8 +32,36 @@ _host.smxh_plan_free.argtypes = [ctypes.c_void_p]
 STATS = ("n_terms", "n_entries", "n_rows", "n_hot", "n_chunks", "padded_fma", "n_levels", "nested", "n_summands", "w_raw", "w_pad")
 
 
+GRADIENT, SPARSE, DENSE = 1, 2, 4  # option bits of smxh_plan_build_opt
+
+
+class _Compact(ctypes.Structure):  # smx_compact_desc
+    _fields_ = [("n_summands", ctypes.c_int64)] + [(name, ctypes.c_void_p) for name in (
+        "n_active", "slot_off", "dims", "degs", "node_off", "node_pool", "quad_pool", "zetas", "val_off", "val_index",
+        "values")] + [("n_values", ctypes.c_int64)]
+
+
+def _compact_desc(layout):
+    desc, keep = _Compact(), []
+    desc.n_summands = len(layout["zetas"])
+    for name, _ in _Compact._fields_[1:-1]:
+        a = np.ascontiguousarray(layout[name], dtype={"n_active": np.int32, "node_pool": np.float64, "quad_pool": np.float64,
+                                                       "values": np.float64}.get(name, np.int64))
+        keep.append(a)
+        setattr(desc, name, a.ctypes.data)
+    desc.n_values = layout["values"].shape[0]
+    return desc, keep
+
+
 class Plan:
-    def __init__(self, layout, d_in, d_out):
+    def __init__(self, layout, d_in, d_out, options=GRADIENT | SPARSE):
+        self.d_out = d_out
+        off = np.ascontiguousarray(np.broadcast_to(np.asarray(layout["offset"], dtype=np.float64), (d_out,)))
+        if layout.get("compact"):
+            desc, self._keep = _compact_desc(layout)
+            self.h = _host.smxh_plan_build_compact(d_in, d_out, off.ctypes.data, ctypes.addressof(desc), options)
+            self._finish()
+            return
         ns = sorted(int(k.split("_")[1]) for k in layout if k.startswith("zetas_"))
         arr = (_Group * max(len(ns), 1))()
         self._keep = []
@@ -40,9 +74,10 @@ class Plan:
             arr[i].n, arr[i].nn = n, F.shape[0]
             for name, v in zip(("tau", "F", "nodes", "weights", "dims", "degs", "zetas"), vals):
                 setattr(arr[i], name, v.ctypes.data)
-        off = np.ascontiguousarray(np.broadcast_to(np.asarray(layout["offset"], dtype=np.float64), (d_out,)))
-        self.d_out = d_out
-        self.h = _host.smxh_plan_build(d_in, d_out, off.ctypes.data, len(ns), ctypes.addressof(arr))
+        self.h = _host.smxh_plan_build_opt(d_in, d_out, off.ctypes.data, len(ns), ctypes.addressof(arr), options)
+        self._finish()
+
+    def _finish(self):
         self.error = None if self.h else _host.smxh_plan_error().decode()
         if self.h:
             st = np.zeros(len(STATS), dtype=np.int64)
@@ -55,6 +90,12 @@ class Plan:
         _host.smxh_plan_eval_host(self.h, x.ctypes.data, len(x), x.shape[1], y.ctypes.data)
         return y
 
+    def dense(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros((len(x), self.d_out))
+        _host.smxh_plan_eval_dense_host(self.h, x.ctypes.data, len(x), x.shape[1], y.ctypes.data)
+        return y
+
     def gradient(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         J = np.zeros((len(x), self.d_out, x.shape[1]))
@@ -64,6 +105,13 @@ class Plan:
     def __del__(self):
         if getattr(self, "h", None):
             _host.smxh_plan_free(self.h)
+
+
+def _layout_of(g, case=None):
+    if any(k.startswith("layout_F_") for k in g.files):
+        return golden_layout(g)
+    kwargs, f = interpolator_inputs(g)
+    return SmolyakBarycentricInterpolator(**kwargs)._assemble(f, {})[0]
 
 
 @pytest.mark.parametrize("case", ALL_CASES)
@@ -136,3 +184,53 @@ def test_plan_rejects_malformed_layouts():
     nodes[:, :, 1] = nodes[:, :, 0]  # duplicate node
     bad[f"nodes_{n}"] = nodes
     assert "distinct" in Plan(bad, g["x"].shape[1], int(g["d_out"])).error
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_dense_form_reproduces_reference_values(case):
+    """The GEMM-regime form (one column of Phi per term, dense coefficient matrix in DMMA fragment order) evaluated on
+    the host in the kernel's order agrees with the reference outputs like the block-sparse form does."""
+    g = load(case)
+    layout = _layout_of(g)
+    d_in, d_out = g["x"].shape[1], int(g["d_out"])
+    plan = Plan(layout, d_in, d_out, options=DENSE)
+    assert plan.error is None, plan.error
+    y = plan.dense(g["x"])
+    assert scaled_error(y, g["y_ref"], g["cond_abs"]) < 1e-12
+    assert scaled_error(y, Plan(layout, d_in, d_out)(g["x"]), g["cond_abs"]) < 1e-13
+
+
+@pytest.mark.parametrize("case", LAYOUT_CASES)
+def test_compact_layout_gives_the_same_plan(case):
+    """smx_create_compact's description (exact shapes, node-indexed values) compiles to the same coefficients as the
+    reference's padded per-group layout, and its host quadrature equals the reference integral."""
+    g = load(case)
+    kwargs, f = interpolator_inputs(g)
+    d_in, d_out = g["x"].shape[1], int(g["d_out"])
+    ip = SmolyakBarycentricInterpolator(**kwargs)
+    compact, evals = ip._assemble_compact(f, {})
+    # one row per function evaluation (the evaluation at the centre lives in `offset` alone for non-nested rules)
+    assert compact["values"].shape in ((ip.n_f_evals, d_out), (ip.n_f_evals - 1, d_out)) and ip.n_f_evals_new == ip.n_f_evals
+    padded, evals_ref = SmolyakBarycentricInterpolator(**kwargs)._assemble(f, {})
+    assert set(evals) == set(evals_ref)
+    a, b = Plan(compact, d_in, d_out, GRADIENT | SPARSE | DENSE), Plan(padded, d_in, d_out, GRADIENT | SPARSE | DENSE)
+    assert a.error is None and b.error is None, (a.error, b.error)
+    assert {k: v for k, v in a.stats.items() if k != "w_pad"} == {k: v for k, v in b.stats.items() if k != "w_pad"}
+    x = g["x"][:64]
+    assert np.array_equal(a(x), b(x)) and np.array_equal(a.dense(x), b.dense(x))
+    assert np.array_equal(a.gradient(x), b.gradient(x))
+    desc, keep = _compact_desc(compact)
+    q = np.zeros(d_out)
+    off = np.ascontiguousarray(np.broadcast_to(np.asarray(compact["offset"], dtype=np.float64), (d_out,)))
+    assert _host.smxh_integrate_compact(d_out, off.ctypes.data, ctypes.addressof(desc), q.ctypes.data) == 0
+    np.testing.assert_allclose(q, g["Q_ref"], rtol=2e-9, atol=2e-9)  # the reference's own summation noise (test_oracle.py)
+
+
+def test_compact_layout_reuses_f_evals():
+    g = load("small_03")
+    kwargs, f = interpolator_inputs(g)
+    ip = SmolyakBarycentricInterpolator(**kwargs)
+    _, evals = ip._assemble_compact(f, {})
+    again = SmolyakBarycentricInterpolator(**kwargs)
+    layout, _ = again._assemble_compact(lambda x: 1 / 0, evals)  # nothing new to evaluate
+    assert again.n_f_evals_new == 0 and layout["values"].shape[0] in (again.n_f_evals, again.n_f_evals - 1)
