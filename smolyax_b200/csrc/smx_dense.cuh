@@ -5,6 +5,7 @@
 namespace smx {
 
 constexpr int kDenseTile = 32;  // points per CTA
+static_assert(kDenseStageK4 == 16 && kDensePadK4 == 32, "stages of 8 or 16 k-steps, two stages of look-ahead");
 
 struct DenseArgs {
     const double* eta;
@@ -16,7 +17,7 @@ struct DenseArgs {
     const double* coef;      // [ceil(d_out / 8)][k4][32] DMMA B fragments
     const double* c0;
     long long N, ldx, d_out;
-    int k4;                  // k-steps (4 terms each)
+    int k4;                  // k-steps (4 terms each), a multiple of kDenseStageK4; arrays carry kDensePadK4 more (zeros)
     int nblk;                // ceil(d_out / 8)
     int n_tab, n_hot_rows, n_levels, hot_dims;
     int level_off[kMaxLevels + 2];

@@ -18,6 +18,7 @@
 //   epilogue   = y[p][o] = c0[o] + acc, 16-byte stores.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "smx_dense.cuh"
 
@@ -30,13 +31,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-template <int NW, int NB, int PF>
-__global__ void __launch_bounds__(NW * 32, 1)
+template <int NW, int NB, int PF, int CTAS>
+__global__ void __launch_bounds__(NW * 32, CTAS)
 dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __restrict__ y) {
     static_assert(NW % PF == 0, "the register ring is indexed with the k-step inside a stage");
     constexpr int kThreads = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* abuf = reinterpret_cast<double*>(smem_raw);       // [2][NW][32 lanes][4]: A fragments of two stages
+    double* abuf = reinterpret_cast<double*>(smem_raw);       // [2][NW][2][32 lanes][2]: A fragments of two stages
     double* tab = abuf + 2 * NW * 128;                         // [n_tab][kTabPitch] value table
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,28 +69,31 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     }
 
     // ---- main loop -----------------------------------------------------------------------------------------------------
-    const int n_stage = (a.k4 + NW - 1) / NW;
-    // this warp's output blocks (8 outputs each)
+    // The host pads the term list to whole stages of 16 k-steps with zero coefficients and appends two more stages of
+    // zeros, so nothing in this loop needs a bounds check: no branch between the DMMAs of a stage.
+    const int n_stage = a.k4 / NW;
+    // this warp's output blocks (8 outputs each); block indices are clamped so that every load has a valid address
     const int jb0 = (blockIdx.y * NW + warp) * NB;
     const int nbv = max(0, min(NB, a.nblk - jb0));
-    const double* bsrc = a.coef + ((size_t)jb0 * a.k4) * 32 + lane;
-    const size_t bstride = (size_t)a.k4 * 32;
+    const size_t bstride = (size_t)(a.k4 + kDensePadK4) * 32;
+    const double* bbase = a.coef + lane;
+    unsigned boff[NB];  // element offsets (the whole matrix has fewer than 2^32 elements: checked at upload)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) boff[j] = (unsigned)((size_t)min(jb0 + j, a.nblk - 1) * bstride);
 
     // A assembly: this thread owns (k-step `warp` of the stage, fragment lane `lane`): term 4 * k4 + tig, points gid + 8 i
-    const double* xr[4];
+    const double* xt = x + p0 * a.ldx;  // this tile's rows; row offsets of the lane's four points fit 32 bits
+    int xoff[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) xr[i] = x + min(p0 + gid + 8 * i, a.N - 1) * a.ldx;
-    auto meta_of = [&](int stage) {
-        const int g = stage * NW + warp;
-        return g < a.k4 ? __ldg(a.meta + 4 * g + tig) : make_int2(0, 0);
-    };
+    for (int i = 0; i < 4; ++i) xoff[i] = (int)(min((long long)(gid + 8 * i), a.N - 1 - p0) * a.ldx);
+    auto meta_of = [&](int stage) { return __ldg(a.meta + 4 * (stage * NW + warp) + tig); };
     double xc[4] = {0.0, 0.0, 0.0, 0.0};
     auto load_cold = [&](int2 m) {  // leading entry on a cold column: pi = x - eta0, straight from x
         if (m.y < 0) {
             const int dim = -1 - m.y;
             const double e0 = __ldg(a.eta0 + dim);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xr[i] + dim) - e0;
+            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim) - e0;
         }
     };
     auto assemble = [&](int2 m, int buf) {
@@ -99,9 +103,10 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
             const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i];
             v[i] = tab[m.x * kTabPitch + gid + 8 * i] * lead;
         }
-        double2* dst = reinterpret_cast<double2*>(abuf + ((buf * NW + warp) * 32 + lane) * 4);
+        // two 16-byte halves per lane, each half contiguous over the lanes: conflict-free stores here and loads below
+        double2* dst = reinterpret_cast<double2*>(abuf + (buf * NW + warp) * 128) + lane;
         dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
+        dst[32] = make_double2(v[2], v[3]);
     };
 
     int2 m1 = meta_of(0);
@@ -120,36 +125,34 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
     for (int u = 0; u < PF; ++u)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) bq[u][j] = (u < a.k4 && j < nbv) ? __ldg(bsrc + j * bstride + (size_t)u * 32) : 0.0;
+        for (int j = 0; j < NB; ++j) bq[u][j] = __ldg(bbase + boff[j] + u * 32);
+
+    auto stage_mma = [&](int s, auto full) {
+        const double2* af = reinterpret_cast<const double2*>(abuf + (s & 1) * NW * 128) + lane;
+        const double* bp = bbase + (size_t)s * NW * 32;
+#pragma unroll
+        for (int kk = 0; kk < NW; ++kk) {
+            const double2 a01 = af[kk * 64], a23 = af[kk * 64 + 32];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (decltype(full)::value || j < nbv) {
+                    dmma(acc[0][j], a01.x, bq[kk % PF][j]);
+                    dmma(acc[1][j], a01.y, bq[kk % PF][j]);
+                    dmma(acc[2][j], a23.x, bq[kk % PF][j]);
+                    dmma(acc[3][j], a23.y, bq[kk % PF][j]);
+                }
+                // refill the slot just consumed: the fragment of k-step kk + PF (no second register set needed)
+                bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
+            }
+        }
+    };
 
     for (int s = 0; s < n_stage; ++s) {
         const int2 m2 = meta_of(s + 2);
         load_cold(m1);  // for stage s + 1; consumed after the DMMAs below
-        if (nbv > 0) {
-            const double* af = abuf + ((s & 1) * NW * 32 + lane) * 4;
-#pragma unroll
-            for (int kk = 0; kk < NW; ++kk) {
-                const int g = s * NW + kk;
-                if (g < a.k4) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(af + kk * 128);
-                    const double2 a23 = *reinterpret_cast<const double2*>(af + kk * 128 + 2);
-                    double b[NB];
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        b[j] = bq[kk % PF][j];
-                        bq[kk % PF][j] = (g + PF < a.k4 && j < nbv) ? __ldg(bsrc + j * bstride + (size_t)(g + PF) * 32) : 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        dmma(acc[0][j], a01.x, b[j]);
-                        dmma(acc[1][j], a01.y, b[j]);
-                        dmma(acc[2][j], a23.x, b[j]);
-                        dmma(acc[3][j], a23.y, b[j]);
-                    }
-                }
-            }
-        }
-        if (s + 1 < n_stage) assemble(m1, (s + 1) & 1);
+        if (nbv == NB) stage_mma(s, std::true_type());
+        else if (nbv > 0) stage_mma(s, std::false_type());
+        assemble(m1, (s + 1) & 1);
         m1 = m2;
         __syncthreads();
     }
@@ -179,17 +182,17 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 
 size_t dense_smem_bytes(int n_tab, int nw) { return sizeof(double) * ((size_t)2 * nw * 128 + (size_t)n_tab * kTabPitch); }
 
-template <int NW, int NB, int PF>
+template <int NW, int NB, int PF, int CTAS>
 int launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
     const size_t smem = dense_smem_bytes(a.n_tab, NW);
     static size_t opted = 0;
     if (smem > opted) {
-        SMX_CUDA(cudaFuncSetAttribute(dense_eval_kernel<NW, NB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMX_CUDA(cudaFuncSetAttribute(dense_eval_kernel<NW, NB, PF, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted = smem;
     }
     const long long tiles = (a.N + kDenseTile - 1) / kDenseTile;
     const int groups = (a.nblk + NW * NB - 1) / (NW * NB);
-    dense_eval_kernel<NW, NB, PF><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
+    dense_eval_kernel<NW, NB, PF, CTAS><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
     SMX_LAUNCH_CHECK("dense_eval_kernel");
     return SMX_OK;
 }
@@ -198,16 +201,27 @@ int launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
 
 bool dense_kernel_fits(int n_tab, int smem_optin) { return dense_smem_bytes(n_tab, 16) <= (size_t)smem_optin; }
 
-// CTA shape: NB output blocks per warp (register tile 32 points x 8 NB outputs), NW warps.  Few outputs: narrow warp
-// tiles so that every warp has work; many outputs: the widest tile (fewest A-fragment loads per DMMA).
+// CTA shape.  Many outputs: 16 warps x 4 output blocks (32 points x 512 outputs per CTA; the widest register tile, fewest
+// A-fragment loads per DMMA).  Few outputs: 8 warps x 1 or 2 blocks with a deeper B ring, two CTAs per SM when the value
+// table leaves room (more independent DMMA chains and loads in flight per SM).
 int dense_kernel_launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
     static const int want_nb = std::getenv("SMX_DENSE_NB") ? std::atoi(std::getenv("SMX_DENSE_NB")) : 0;
     static const int want_nw = std::getenv("SMX_DENSE_NW") ? std::atoi(std::getenv("SMX_DENSE_NW")) : 0;
-    int nb = want_nb ? want_nb : (a.nblk >= 48 ? 4 : a.nblk > 16 ? 2 : 1);
-    int nw = want_nw ? want_nw : std::min(16, std::max(8, ((a.nblk + nb - 1) / nb + 3) / 4 * 4));
-    if (nb == 4) return nw <= 8 ? launch<8, 4, 2>(a, x, y, st) : launch<16, 4, 2>(a, x, y, st);
-    if (nb == 2) return nw <= 8 ? launch<8, 2, 4>(a, x, y, st) : nw <= 12 ? launch<12, 2, 4>(a, x, y, st) : launch<16, 2, 4>(a, x, y, st);
-    return nw <= 8 ? launch<8, 1, 4>(a, x, y, st) : nw <= 12 ? launch<12, 1, 4>(a, x, y, st) : launch<16, 1, 4>(a, x, y, st);
+    static const int want_ctas = std::getenv("SMX_DENSE_CTAS") ? std::atoi(std::getenv("SMX_DENSE_CTAS")) : 0;
+    int device = 0, smem_sm = 0;
+    SMX_CUDA(cudaGetDevice(&device));
+    SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    const int nb = want_nb ? want_nb : (a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1);
+    const int nw = want_nw ? want_nw : (nb == 4 ? 16 : 8);
+    const bool two_fit = 2 * (dense_smem_bytes(a.n_tab, 8) + 1024) <= (size_t)smem_sm;
+    const int ctas = want_ctas ? want_ctas : (two_fit ? 2 : 1);
+    if (nb == 4) return nw <= 8 ? launch<8, 4, 4, 1>(a, x, y, st) : launch<16, 4, 2, 1>(a, x, y, st);
+    if (nb == 2) {
+        if (nw > 8) return launch<16, 2, 4, 1>(a, x, y, st);
+        return ctas == 2 && two_fit ? launch<8, 2, 8, 2>(a, x, y, st) : launch<8, 2, 8, 1>(a, x, y, st);
+    }
+    if (nw > 8) return launch<16, 1, 8, 1>(a, x, y, st);
+    return ctas == 2 && two_fit ? launch<8, 1, 8, 2>(a, x, y, st) : launch<8, 1, 8, 1>(a, x, y, st);
 }
 
 }  // namespace smx

@@ -78,7 +78,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(plan.c0, &dev.c0, dev.bytes))) return rc;
     if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
-    if (plan.has_dense && dense_kernel_fits(plan.n_tab, smem_optin)) {
+    // (the kernel addresses the dense matrix with 32-bit element offsets)
+    if (plan.has_dense && dense_kernel_fits(plan.n_tab, smem_optin) && plan.dense_coef.size() < (size_t)UINT32_MAX) {
         dev.dense_k4 = plan.dense_k4;
         if ((rc = upload(plan.dense_meta, &dev.dense_meta, dev.bytes, 2))) return rc;
         if ((rc = upload(plan.dense_eta0, &dev.dense_eta0, dev.bytes))) return rc;

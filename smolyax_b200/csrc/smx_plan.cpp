@@ -604,13 +604,14 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     // ---- 9a. dense form ------------------------------------------------------------------------------------------------
     if (opt.dense) {
         const int64_t K = (int64_t)nz.size();
-        plan.dense_k4 = (int32_t)((K + 3) / 4);
-        plan.dense_meta.assign((size_t)plan.dense_k4 * 8, 0);  // padding terms: ones row * ones row, zero coefficients
+        plan.dense_k4 = (int32_t)(((K + 3) / 4 + kDenseStageK4 - 1) / kDenseStageK4 * kDenseStageK4);
+        const int64_t k4s = plan.dense_k4 + kDensePadK4;       // allocated k-steps
+        plan.dense_meta.assign((size_t)k4s * 8, 0);            // padding terms: ones row * ones row, zero coefficients
         plan.dense_eta0.assign((size_t)d_in, 0.0);
         for (int64_t d = 0; d < d_in; ++d)
             if (maxdeg[d] > 0) plan.dense_eta0[d] = plan.eta[eta_off[d]];
         const int64_t nblk = (d_out + 7) / 8;
-        plan.dense_coef.assign((size_t)nblk * plan.dense_k4 * 32, 0.0);
+        plan.dense_coef.assign((size_t)nblk * k4s * 32, 0.0);
         for (int64_t i = 0; i < K; ++i) {
             const int32_t e = nz[i].block * kBlockWidth + nz[i].lane;
             plan.dense_meta[2 * i] = nz[i].row;
@@ -618,7 +619,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             const int64_t k4 = i >> 2, tig = i & 3;
             const ld* src = &C[(size_t)nz[i].term * d_out];
             for (int64_t o = 0; o < d_out; ++o)
-                plan.dense_coef[(size_t)(((o >> 3) * plan.dense_k4 + k4) * 32 + 4 * (o & 7) + tig)] = (double)src[o];
+                plan.dense_coef[(size_t)(((o >> 3) * k4s + k4) * 32 + 4 * (o & 7) + tig)] = (double)src[o];
         }
         plan.has_dense = true;
     }
@@ -805,7 +806,7 @@ void eval_plan_dense_host(const FastPlan& plan, const double* x, int64_t N, int6
             for (int64_t i = 0; i < 4 * (int64_t)plan.dense_k4; ++i) {
                 const int32_t ia = plan.dense_meta[2 * i], ib = plan.dense_meta[2 * i + 1];
                 const double phi = tab[ia] * (ib >= 0 ? tab[ib] : xp[-1 - ib] - plan.dense_eta0[-1 - ib]);
-                acc = std::fma(phi, plan.dense_coef[(size_t)(((o >> 3) * plan.dense_k4 + (i >> 2)) * 32 + 4 * (o & 7) + (i & 3))], acc);
+                acc = std::fma(phi, plan.dense_coef[(size_t)(((o >> 3) * (plan.dense_k4 + kDensePadK4) + (i >> 2)) * 32 + 4 * (o & 7) + (i & 3))], acc);
             }
             yp[o] = plan.c0[o] + acc;
         }

@@ -66,6 +66,8 @@ constexpr int kChunkRows = 16;     // rows per work item
 constexpr int kMaxLevels = 16;
 
 constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
+constexpr int kDenseStageK4 = 16;  // dense form: the term list is padded to whole stages of 16 k-steps (64 terms) ..
+constexpr int kDensePadK4 = 32;    // .. and every array carries two more stages of zeros (look-ahead without bounds checks)
 constexpr int kTabPitch = 36;      // doubles per value-table row in shared memory (32 points + 32 bytes of skew:
                                    // rows r, r' with r != r' (mod 4) never share a bank in the DMMA A-fragment loads)
 
@@ -136,12 +138,12 @@ struct FastPlan {
     // Phi[p][t] = tab[hot part of t][p] * pi_{leading entry of t}(x_p)  and  C (terms x d_out).  Terms are ordered hot
     // entries first (by block, row), then by column of x; padded with zero rows to whole k-steps of 4 terms.
     bool has_dense = false;
-    int32_t dense_k4 = 0;                // k-steps
+    int32_t dense_k4 = 0;                // k-steps, a multiple of kDenseStageK4; the arrays hold kDensePadK4 more (zeros)
     std::vector<int32_t> dense_meta;     // 2 ints per term: table row of the hot part; table row of the leading entry
                                          // (hot) or  -1 - column of x  (cold: pi = x - eta0[column])
     std::vector<double> dense_eta0;      // (d_in) first centre of every dimension
-    std::vector<double> dense_coef;      // [ceil(d_out / 8)][dense_k4][32]: DMMA B fragments, lane = 4 * gid + tig holds
-                                         // C[4 * k4 + tig][8 * jb + gid]
+    std::vector<double> dense_coef;      // [ceil(d_out / 8)][dense_k4 + kDensePadK4][32]: DMMA B fragments, lane = 4 * gid + tig
+                                         // holds C[4 * k4 + tig][8 * jb + gid]
 };
 
 struct PlanOptions {

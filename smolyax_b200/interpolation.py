@@ -189,7 +189,11 @@ class SmolyakBarycentricInterpolator:
         row_of, row_src, new_points = {}, [], []  # evaluation -> row of `values`; its value or None (pending)
         n_active, slot_dims, slot_degs, slot_nodes, zetas, val_off, val_index = [], [], [], [], [], [0], []
 
-        for s in range(len(lengths)):
+        # summands in the order of the reference layout (groups by number of active dimensions in order of first
+        # appearance, the reference's walk inside a group): both create entries then add up the same numbers in the same
+        # order and the two kinds of handle agree bit for bit
+        groups = sorted(set(lengths.tolist()), key=lambda v: np.flatnonzero(lengths == v)[0])
+        for s in (int(i) for n_grp in groups for i in np.flatnonzero(lengths == n_grp)):
             n = int(lengths[s])
             dims_in = dims_all[offsets[s]:offsets[s + 1]].astype(np.int64)
             degs_in = degs_all[offsets[s]:offsets[s + 1]].astype(np.int64)

@@ -256,7 +256,10 @@ def test_compact_layout_handle(case):
     J_ref = g["J_ref"]
     xs = x[: len(J_ref)]
     J, J2 = ip.gradient(xs), ref.gradient(xs)
-    assert np.array_equal(np.isnan(J), np.isnan(J2)) and np.array_equal(np.nan_to_num(J), np.nan_to_num(J2))
+    # (blocks whose rows are split over several work items add their partial derivatives with atomics: the order of the
+    # additions, hence the last bits, may differ between two runs of the same handle)
+    scale = max(1.0, float(np.nanmax(np.abs(J2))))
+    assert np.array_equal(np.isnan(J), np.isnan(J2)) and np.max(np.abs(np.nan_to_num(J) - np.nan_to_num(J2))) <= 1e-13 * scale
     Q_ld = long_double(g, "Q")
     err_new = np.max(np.abs((ip.integral() - Q_ld).astype(float)))
     err_ref = np.max(np.abs((g["Q_ref"] - Q_ld).astype(float)))
