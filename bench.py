@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="points", choices=["points", "columns"],
+                    help="multi-GPU partition: points (weak scaling, tables replicated) or output columns (strong scaling: "
+                         "every rank evaluates all points for its slice of the value table; for huge d_out)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -193,14 +196,21 @@ def main():
     # ---- set-up: rank 0 evaluates f and assembles the tables once, NCCL broadcast, one device handle per rank ----
     ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=d_out, device=local,
                                         batched_f=True)
-    compact = d_out > 256  # the padded reference layout of cfg3 (29 GB) cannot be assembled: smx_create_compact
+    columns = args.shard == "columns" and world > 1
+    compact = d_out > 256 or columns  # the padded reference layout of cfg3 (29 GB) cannot be assembled: smx_create_compact
     layout = (ip._assemble_compact if compact else ip._assemble)(wl.target(), {})[0] if rank == 0 else None
-    layout = sdist.broadcast_layout(layout, src=0)
+    col_lo, col_hi = 0, d_out
+    if columns:
+        col_lo, col_hi = sdist.shard_columns(d_out, rank, world)
+        layout = sdist.scatter_columns(layout, d_out, src=0)
+        ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=col_hi - col_lo, device=local)
+    else:
+        layout = sdist.broadcast_layout(layout, src=0)
     ip.set_layout(layout)
     info = ip.device_info()
 
     # ---- synthetic inputs, resident in HBM ---------------------------------------------------------------------
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + (0 if columns else rank))  # column shards see the same points
     x = torch.empty((n_points, d_in), dtype=torch.float64, device="cuda")
     if wl.rule == "leja":
         x.uniform_(-1.0, 1.0, generator=gen)
@@ -229,7 +239,7 @@ def main():
     launches = int(_lib.lib.smx_launch_count() - launches0)
     elapsed_ms = sdist.max_over_ranks(start.elapsed_time(stop))
     ms_per_step = elapsed_ms / args.steps
-    value = world * n_points * d_out / (ms_per_step * 1e-3)
+    value = (1 if columns else world) * n_points * d_out / (ms_per_step * 1e-3)
 
     # ---- parity spot check of what was just timed (rank 0): first rows against the CPU oracle ------------------
     parity = None
@@ -240,7 +250,10 @@ def main():
         xs = x[:64].cpu().numpy()
         ref = oracle.evaluate(check_layout, xs)
         got = y[:64].cpu().numpy()
-        parity = float(np.max(np.abs((got if cols is None else got[:, cols]) - ref) / np.maximum(np.abs(ref), 1e-300)))
+        if cols is not None:
+            keep = (cols >= col_lo) & (cols < col_hi)  # rank 0's column shard
+            got, ref = got[:, cols[keep] - col_lo], ref[:, keep]
+        parity = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
 
     # ---- end to end through the public API from pinned host memory ------------------------------------------------
     x_host = torch.empty((n_points, d_in), dtype=torch.float64, pin_memory=True)
@@ -252,12 +265,13 @@ def main():
         y_host = ip(x_host)
     torch.cuda.synchronize()
     e2e_s = sdist.max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-    e2e_value = world * n_points * d_out / e2e_s
-    assert y_host.shape == (n_points, d_out)
+    e2e_value = (1 if columns else world) * n_points * d_out / e2e_s
+    assert y_host.shape == (n_points, col_hi - col_lo)
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        alg_bytes = 8.0 * (d_in + d_out) * n_points  # bytes_eval = 8 (d_in + d_out) per point
+        d_loc = col_hi - col_lo  # outputs this rank's kernel launch produces
+        alg_bytes = 8.0 * (d_in + d_loc) * n_points  # bytes_eval = 8 (d_in + d_out) per point
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         traffic = None
         tfile = ROOT / "profiles" / "traffic.json"
@@ -268,7 +282,7 @@ def main():
                 traffic = None
         dense = bool(info["has_dense_path"])
         fma_per_eval = info["dense_terms"] if dense else info["padded_fma"]
-        fp64_tflops = 2.0 * fma_per_eval * d_out * n_points / (ms_per_step * 1e-3) / 1e12
+        fp64_tflops = 2.0 * fma_per_eval * d_loc * n_points / (ms_per_step * 1e-3) / 1e12
         fp64_peak = None
         try:
             fp64_peak = json.loads((ROOT / "profiles" / "fp64_peaks.json").read_text())["fp64_dmma_tflops"]
@@ -286,7 +300,7 @@ def main():
             # GEMM regime (folded form): algorithmic flops = 2 * d_out * n_terms per point, on the FP64 tensor
             # instruction; the denominator is the FP64 DMMA rate measured on this GPU type (profiles/fp64_peaks.json) -
             # MEASURED_PEAKS.json only carries the bf16 tensor rate, which no fp64 path can use.
-            alg_flops = 2.0 * info["n_terms"] * d_out * n_points
+            alg_flops = 2.0 * info["n_terms"] * d_loc * n_points
             tf = alg_flops / (ms_per_step * 1e-3) / 1e12
             roofline = {
                 "bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
@@ -296,17 +310,19 @@ def main():
             }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{args.config}: {wl.rule} d_in={d_in} d_out={d_out} n={wl.n_target} "
                             f"({info['n_summands']} summands, {info['n_terms']} terms), {n_points} points per GPU",
-                "points_per_gpu": n_points, "parallelism": f"dp{world} (points sharded, tables replicated)",
+                "points_per_gpu": n_points,
+                "parallelism": f"dp{world} (output columns sharded, every rank sees all points)" if columns
+                               else f"dp{world} (points sharded, tables replicated)",
                 "l2": f"inputs + outputs ({8e-9 * (d_in + d_out) * n_points:.1f} GB per step) exceed L2 (126 MB); no flush needed",
             },
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * d_in * n_points,
-                    "d2h_bytes_per_step": 8 * d_out * n_points, "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
+                    "d2h_bytes_per_step": 8 * (col_hi - col_lo) * n_points, "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "parity_max_rel_vs_oracle_first64": parity,

@@ -1,4 +1,6 @@
-"""Multi-GPU plumbing for the evaluation path: one process per GPU, points partitioned, tables replicated.
+"""Multi-GPU plumbing for the evaluation path: one process per GPU, points partitioned, tables replicated - or, when
+``d_out`` is huge, output columns partitioned (``shard_columns`` / ``scatter_columns`` / ``gather_columns``): every rank
+sees all points and owns a contiguous block of outputs, i.e. a column slice of the value table.
 
 The path shards by evaluation point with no per-call collective: rank r evaluates the contiguous
 row block ``shard_rows(N, r, world)`` of ``x``.  The only exchange is at set-up: rank 0 evaluates the target function
@@ -58,6 +60,81 @@ def broadcast_layout(layout, src: int = 0):
             out[k] = flat[pos:pos + n].reshape(shp).copy()
             pos += n
     return out
+
+
+def shard_columns(d_out: int, rank: int, world: int, align: int = 8):
+    """Contiguous partition of the output columns into blocks whose boundaries are multiples of ``align`` (8 = one
+    DMMA output block of the GEMM-regime kernel): returns ``(start, stop)`` of this rank's block (may be empty)."""
+    blocks = -(-int(d_out) // align)
+    lo, hi = shard_rows(blocks, rank, world)
+    return min(lo * align, d_out), min(hi * align, d_out)
+
+
+def column_slice(layout: dict, lo: int, hi: int) -> dict:
+    """The tables of outputs ``lo:hi`` only: a layout (compact or reference form) for an interpolator with
+    ``d_out = hi - lo``.  The interpolant is linear in ``f``, so the slice evaluates exactly the sliced outputs."""
+    out = dict(layout)
+    off = np.asarray(layout["offset"], dtype=float).reshape(-1)
+    out["offset"] = np.full(hi - lo, off[0]) if off.size == 1 else np.ascontiguousarray(off[lo:hi])
+    if layout.get("compact"):
+        out["values"] = np.ascontiguousarray(layout["values"][:, lo:hi])
+    else:
+        for key in layout:
+            if key.startswith("F_"):
+                out[key] = np.ascontiguousarray(layout[key][:, lo:hi])
+    return out
+
+
+def scatter_columns(layout, d_out: int, src: int = 0) -> dict:
+    """Column-sharded set-up for huge ``d_out``: ``src`` holds the full COMPACT layout, every rank receives the index
+    arrays (broadcast, small) and only its own ``shard_columns`` slice of the value table (one scatter).
+    Ranks other than ``src`` pass ``None``.  Returns the rank's ``column_slice``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return column_slice(layout, 0, d_out)
+    rank, world, dev = dist.get_rank(), dist.get_world_size(), _device_for_backend()
+    small = None
+    if rank == src:
+        assert layout.get("compact"), "column sharding ships the compact layout (smx_create_compact)"
+        small = {k: v for k, v in layout.items() if k not in ("values", "offset")}
+        small["n_values"] = np.asarray(layout["values"].shape[0])
+    small = broadcast_layout(small, src=src)
+    n_values = int(small.pop("n_values"))
+    bounds = [shard_columns(d_out, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in bounds)
+    lo, hi = bounds[rank]
+    # values and offset travel together: row 0 = offset slice, rows 1.. = value rows, padded to the widest shard
+    recv = torch.empty((n_values + 1, max(width, 1)), dtype=torch.float64, device=dev)
+    parts = None
+    if rank == src:
+        off = np.broadcast_to(np.asarray(layout["offset"], dtype=float), (d_out,))
+        parts = []
+        for a, b in bounds:
+            blk = np.zeros((n_values + 1, max(width, 1)))
+            blk[0, : b - a] = off[a:b]
+            blk[1:, : b - a] = layout["values"][:, a:b]
+            parts.append(torch.from_numpy(blk).to(dev))
+    dist.scatter(recv, parts, src=src)
+    got = recv.cpu().numpy()
+    out = dict(small)
+    out["compact"] = True
+    out["n_active"] = out["n_active"].astype(np.int32)
+    out["offset"] = got[0, : hi - lo].copy()
+    out["values"] = np.ascontiguousarray(got[1:, : hi - lo])
+    return out
+
+
+def gather_columns(y_local: torch.Tensor, d_out: int) -> torch.Tensor:
+    """Replicated ``(N, d_out)`` result from the column shards (optional: the per-call path itself has no collective)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return y_local
+    world = dist.get_world_size()
+    bounds = [shard_columns(d_out, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in bounds)
+    pad = torch.zeros((y_local.shape[0], width), dtype=y_local.dtype, device=y_local.device)
+    pad[:, : y_local.shape[1]] = y_local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:, : hi - lo] for p, (lo, hi) in zip(parts, bounds)], dim=1)
 
 
 def max_over_ranks(value: float) -> float:
