@@ -22,8 +22,9 @@ from smolyax_b200 import workloads  # noqa: E402
 from smolyax_b200.interpolation import SmolyakBarycentricInterpolator  # noqa: E402
 
 # (config, d_out override, eval points, gradient points)
-CASES = [("cfg1", None, 10_000, 10_000), ("cfg2", None, 1_000_000, 2_000), ("cfg3", 64, 100_000, 2_000),
-         ("cfg3", None, 100_000, 0), ("cfg4", None, 100_000, 1_000), ("cfg5", None, 1_000_000, 200)]
+# (gradient batches are sized to fill the GPU: >= 148 tiles of 32 points, J of at most a few GB)
+CASES = [("cfg1", None, 10_000, 10_000), ("cfg2", None, 1_000_000, 37_888), ("cfg3", 64, 100_000, 9_472),
+         ("cfg3", None, 100_000, 0), ("cfg4", None, 100_000, 9_472), ("cfg5", None, 1_000_000, 4_736)]
 DMMA_PEAK_TFLOPS = 37.12  # profiles/fp64_peaks.json
 
 
@@ -83,8 +84,9 @@ def main():
         if n_grad:
             xg = x[:n_grad]
             ms = timed(lambda: ip.gradient(xg), max(2, args.reps // 2))
-            lines.append({**base, "op": "gradient", "points": n_grad, "ms": ms, "value": n_grad * wl.d_out * wl.d_in / ms * 1e3,
-                          "unit": "J entries/s", "points_per_s": n_grad / ms * 1e3})
+            lines.append({**base, "op": "gradient", "kernel": "dense" if info["dense_grad_columns"] else "sparse", "points": n_grad,
+                          "ms": ms, "value": n_grad * wl.d_out * wl.d_in / ms * 1e3, "unit": "J entries/s",
+                          "points_per_s": n_grad / ms * 1e3, "j_write_gbs": 8.0 * n_grad * wl.d_out * wl.d_in / ms / 1e6})
         ms = timed(lambda: ip.integral(), args.reps)
         lines.append({**base, "op": "integral", "ms": ms, "value": 1e3 / ms, "unit": "calls/s"})
         for ln in lines[first:]:

@@ -59,7 +59,8 @@ typedef struct {
                                        node, instead of the NaN the reference produces there (barycentric.py:152-154) */
 
 #define SMX_DENSE_PATH 8u     /* build the GEMM-regime form (dense term matrix, FP64 tensor instruction) even for small d_out */
-#define SMX_NO_DENSE_PATH 16u /* never build it; default: built when d_out >= 32 (DESIGN.md "K2") */
+#define SMX_NO_DENSE_PATH 16u /* never build it; default: values use it when d_out >= 32, the gradient when there are at
+                                 least 32 derivative columns (d_out x hot dimensions)  (DESIGN.md "K2") */
 
 typedef struct {
     int64_t d_in;
@@ -163,7 +164,9 @@ typedef struct {
     int64_t device_bytes;   /* HBM held by the handle */
     int32_t has_fast_path, has_groups, nested;
     int32_t has_dense_path; /* GEMM-regime form present: smx_eval uses it */
-    int64_t dense_terms;    /* its K (terms, padded to whole k-steps of 4) */
+    int64_t dense_terms;    /* its K (terms, padded to whole stages of 64) */
+    int64_t dense_grad_columns; /* > 0: smx_gradient computes that many derivative sets (d_out x hot dimensions) as columns
+                                   of the same dense product */
 } smx_info;
 int smx_get_info(const smx_interp* h, smx_info* info);
 

@@ -118,6 +118,7 @@ PlanOptions plan_options(uint32_t flags, int64_t d_out, bool sparse_wanted) {
     // only costs memory once the dense form exists (it would still serve the gradient)
     opt.sparse = sparse_wanted && !(opt.dense && d_out > 2048);
     opt.gradient = opt.sparse;
+    opt.dense_gradient = (flags & SMX_NO_DENSE_PATH) ? 0 : (flags & SMX_DENSE_PATH) ? 1 : -1;
     return opt;
 }
 
@@ -138,6 +139,7 @@ int adopt_plan(smx_interp* h, const FastPlan& plan) {
     h->info.device_bytes += h->fast.bytes;
     h->info.has_dense_path = h->fast.has_dense;
     h->info.dense_terms = 4ll * h->fast.dense_k4;
+    h->info.dense_grad_columns = h->fast.has_dense_grad ? h->d_out * h->fast.n_gd : 0;
     return SMX_OK;
 }
 

@@ -93,6 +93,11 @@ struct FastDevice {
     int32_t* dense_meta = nullptr;
     double* dense_eta0 = nullptr;
     double* dense_coef = nullptr;
+    bool has_cold = false;          // some leading entries live on cold columns (their derivatives are block-sparse row sums)
+    bool has_dense_grad = false;    // derivative sets as dense columns: smx_gradient = sparse kernel (cold columns) + dense kernel
+    double* dense_grad_coef = nullptr;
+    double* dense_grad_c0 = nullptr;
+    int32_t* dense_grad_col = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)

@@ -15,10 +15,13 @@ struct DenseArgs {
     const int2* meta;        // per term: (table row of the hot part, table row of the leading entry or -1 - column of x)
     const double* eta0;      // (d_in) first centre of every dimension
     const double* coef;      // [ceil(d_out / 8)][k4][32] DMMA B fragments
-    const double* c0;
-    long long N, ldx, d_out;
+    const double* c0;        // (ncol) constant term per column
+    const int32_t* colmap;   // NULL: column c of the product is column c of y;  else its position inside a row of y (gradient)
+    long long N, ldx;
+    long long ncol;          // columns of the product: d_out (values) or d_out * n_gd (derivative sets)
+    long long ldy;           // row pitch of y in elements: d_out (values) or d_out * d_in (gradient)
     int k4;                  // k-steps (4 terms each), a multiple of kDenseStageK4; arrays carry kDensePadK4 more (zeros)
-    int nblk;                // ceil(d_out / 8)
+    int nblk;                // ceil(ncol / 8)
     int n_tab, n_hot_rows, n_levels, hot_dims;
     int level_off[kMaxLevels + 2];
 };

@@ -158,23 +158,25 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------------------------
-    const bool vec = (a.d_out & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool vec = a.colmap == nullptr && (a.ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
         if (j >= nbv) break;
         const long long col = 8ll * (jb0 + j) + 2 * tig;
-        if (col >= a.d_out) continue;
-        const double c0a = __ldg(a.c0 + col), c0b = col + 1 < a.d_out ? __ldg(a.c0 + col + 1) : 0.0;
+        if (col >= a.ncol) continue;
+        const bool two = col + 1 < a.ncol;
+        const double c0a = __ldg(a.c0 + col), c0b = two ? __ldg(a.c0 + col + 1) : 0.0;
+        const long long ya = a.colmap ? __ldg(a.colmap + col) : col, yb = a.colmap && two ? __ldg(a.colmap + col + 1) : col + 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const long long p = p0 + gid + 8 * i;
             if (p >= a.N) continue;
-            double* dst = y + p * a.d_out + col;
+            double* dst = y + p * a.ldy;
             if (vec) {
-                *reinterpret_cast<double2*>(dst) = make_double2(c0a + acc[i][j][0], c0b + acc[i][j][1]);
+                *reinterpret_cast<double2*>(dst + ya) = make_double2(c0a + acc[i][j][0], c0b + acc[i][j][1]);
             } else {
-                dst[0] = c0a + acc[i][j][0];
-                if (col + 1 < a.d_out) dst[1] = c0b + acc[i][j][1];
+                dst[ya] = c0a + acc[i][j][0];
+                if (two) dst[yb] = c0b + acc[i][j][1];
             }
         }
     }

@@ -62,8 +62,10 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if (plan.n_levels > kMaxLevels) return fail(SMX_ERR_UNSUPPORTED, "too many active dimensions per term");
     for (size_t l = 0; l < plan.level_off.size() && l < (size_t)kMaxLevels + 2; ++l) dev.level_off[l] = plan.level_off[l];
     bool sparse_ok = plan.has_sparse;
-    for (int32_t c = 0; c < plan.n_chunks; ++c)
+    for (int32_t c = 0; c < plan.n_chunks; ++c) {
         if (!(plan.chunk_flags[c] & (kChunkHot | kChunkContig))) sparse_ok = false;
+        if (!(plan.chunk_flags[c] & kChunkHot)) dev.has_cold = true;
+    }
     int device = 0, smem_optin = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&dev.sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -79,12 +81,23 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
     // (the kernel addresses the dense matrix with 32-bit element offsets)
-    if (plan.has_dense && dense_kernel_fits(plan.n_tab, smem_optin) && plan.dense_coef.size() < (size_t)UINT32_MAX) {
+    if ((plan.has_dense || plan.has_dense_grad) && dense_kernel_fits(plan.n_tab, smem_optin) &&
+        plan.dense_coef.size() < (size_t)UINT32_MAX && plan.dense_grad_coef.size() < (size_t)UINT32_MAX) {
         dev.dense_k4 = plan.dense_k4;
         if ((rc = upload(plan.dense_meta, &dev.dense_meta, dev.bytes, 2))) return rc;
         if ((rc = upload(plan.dense_eta0, &dev.dense_eta0, dev.bytes))) return rc;
-        if ((rc = upload(plan.dense_coef, &dev.dense_coef, dev.bytes))) return rc;
-        dev.has_dense = true;
+        if (plan.has_dense) {
+            if ((rc = upload(plan.dense_coef, &dev.dense_coef, dev.bytes))) return rc;
+            dev.has_dense = true;
+        }
+        if (plan.has_dense_grad && sparse_ok) {  // (the cold columns of J come from the block-sparse kernel)
+            if ((rc = upload(plan.dense_grad_coef, &dev.dense_grad_coef, dev.bytes))) return rc;
+            if ((rc = upload(plan.dense_grad_c0, &dev.dense_grad_c0, dev.bytes))) return rc;
+            if ((rc = upload(plan.dense_grad_col, &dev.dense_grad_col, dev.bytes))) return rc;
+            dev.has_dense_grad = true;
+        }
+    } else if (plan.has_dense_grad) {
+        return fail(SMX_ERR_UNSUPPORTED, "value table does not fit in shared memory");  // (the sparse sets were not built)
     }
     if (!sparse_ok) {
         if (!dev.has_dense)
@@ -140,7 +153,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
     dev.n_sets = plan.n_sets;
     dev.n_gd = (int32_t)plan.grad_dims.size();
-    dev.grad_ok = plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) && (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0);
+    dev.grad_ok = dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
+                                         (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0));
     if ((rc = upload(plan.grad_dims, &dev.grad_dims, dev.bytes))) return rc;
     dev.has_sparse = true;
     return SMX_OK;
@@ -148,7 +162,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
 
 void fast_free(FastDevice& d) {
     void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0,
-                    d.grad_dims, d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef};
+                    d.grad_dims, d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef,
+                    d.dense_grad_coef, d.dense_grad_c0, d.dense_grad_col};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -198,7 +213,7 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.d_out = d.d_out;
     a.num_tiles = (N + kTile - 1) / kTile;
     a.gradient = gradient;
-    a.n_gd = d.n_gd;
+    a.n_gd = d.has_dense_grad ? 0 : d.n_gd;  // dense derivative columns: this kernel only runs the function's own sets
     a.grad_dims = d.grad_dims;
     a.d_in = d.d_in;
     a.n_hot = d.n_hot;
@@ -223,9 +238,9 @@ int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     return run_fast(d, x, N, ldx, y, 0, st);
 }
 
-int dense_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
-    if (N == 0) return SMX_OK;
-    if (!d.has_dense) return fail(SMX_ERR_UNSUPPORTED, "plan has no dense form");
+namespace {
+
+int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, bool gradient, cudaStream_t st) {
     DenseArgs a;
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
@@ -233,19 +248,29 @@ int dense_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, dou
     a.hot_pos = d.hot_pos;
     a.meta = reinterpret_cast<const int2*>(d.dense_meta);
     a.eta0 = d.dense_eta0;
-    a.coef = d.dense_coef;
-    a.c0 = d.c0;
+    a.coef = gradient ? d.dense_grad_coef : d.dense_coef;
+    a.c0 = gradient ? d.dense_grad_c0 : d.c0;
+    a.colmap = gradient ? d.dense_grad_col : nullptr;
     a.N = N;
     a.ldx = ldx;
-    a.d_out = d.d_out;
+    a.ncol = gradient ? d.d_out * d.n_gd : d.d_out;
+    a.ldy = gradient ? d.d_out * d.d_in : d.d_out;
     a.k4 = d.dense_k4;
-    a.nblk = (int)((d.d_out + 7) / 8);
+    a.nblk = (int)((a.ncol + 7) / 8);
     a.n_tab = d.n_tab;
     a.n_hot_rows = d.n_hot_rows;
     a.n_levels = d.n_levels;
     a.hot_dims = d.hot_dims;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
-    return dense_kernel_launch(a, x, y, st);
+    return dense_kernel_launch(a, x, out, st);
+}
+
+}  // namespace
+
+int dense_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
+    if (N == 0) return SMX_OK;
+    if (!d.has_dense) return fail(SMX_ERR_UNSUPPORTED, "plan has no dense form");
+    return run_dense(d, x, N, ldx, y, false, st);
 }
 
 int fast_gradient(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st) {
@@ -253,8 +278,11 @@ int fast_gradient(const FastDevice& d, const double* x, int64_t N, int64_t ldx, 
     if (!d.has_sparse || !d.grad_ok) return fail(SMX_ERR_UNSUPPORTED, "plan has no derivative sets");
     // dimensions without any entry keep derivative zero; everything else is written by the kernel
     SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * d.d_out * d.d_in, st));
-    int rc = run_fast(d, x, N, ldx, J, 1, st);
-    if (rc) return rc;
+    // block-sparse kernel: derivatives w.r.t. the cold columns (row sums) and, unless they are dense columns, the
+    // derivative sets of the hot dimensions; dense kernel: the derivative sets as columns of Phi G
+    int rc = SMX_OK;
+    if ((!d.has_dense_grad || d.has_cold) && (rc = run_fast(d, x, N, ldx, J, 1, st))) return rc;
+    if (d.has_dense_grad && (rc = run_dense(d, x, N, ldx, J, true, st))) return rc;
     if (nan_at_nodes) {
         const long long total = (long long)N * d.d_in;
         const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)d.sm_count * 16);

@@ -219,7 +219,7 @@ std::string integrate_compact(int64_t d_out, const double* offset, const Compact
 
 static std::string build_from_summands(int64_t d_in, int64_t d_out, const double* offset, std::vector<Summand>& summands,
                                        int64_t w_pad, FastPlan& plan, const PlanOptions& opt) {
-    const bool with_gradient = opt.gradient && opt.sparse;
+    const bool with_gradient = opt.gradient && opt.sparse;  // (the cold derivatives always come from the sparse form)
     plan = FastPlan();
     plan.d_in = d_in;
     plan.d_out = d_out;
@@ -531,7 +531,10 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         }
     }
     const int64_t n_gd = (int64_t)plan.grad_dims.size();
-    plan.n_sets = (int32_t)(d_out * (1 + n_gd));
+    // derivative sets as columns of the dense product instead of block-sparse sets: worthwhile from a few dozen columns
+    const bool dense_grad = opt.dense_gradient != 0 && n_gd > 0 && (opt.dense_gradient == 1 || d_out * n_gd >= 32) &&
+                            (double)d_out * (double)n_gd * (double)T * 8.0 <= 3.0e9;
+    plan.n_sets = (int32_t)(d_out * (1 + (dense_grad ? 0 : n_gd)));
     // coefficient of term t in set s
     auto coef_of = [&](int32_t t, int64_t set) -> double {
         if (set < d_out) return (double)C[(size_t)t * d_out + set];
@@ -602,7 +605,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         return a.lane < b.lane;
     });
     // ---- 9a. dense form ------------------------------------------------------------------------------------------------
-    if (opt.dense) {
+    if (opt.dense || dense_grad) {
         const int64_t K = (int64_t)nz.size();
         plan.dense_k4 = (int32_t)(((K + 3) / 4 + kDenseStageK4 - 1) / kDenseStageK4 * kDenseStageK4);
         const int64_t k4s = plan.dense_k4 + kDensePadK4;       // allocated k-steps
@@ -610,7 +613,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         plan.dense_eta0.assign((size_t)d_in, 0.0);
         for (int64_t d = 0; d < d_in; ++d)
             if (maxdeg[d] > 0) plan.dense_eta0[d] = plan.eta[eta_off[d]];
-        const int64_t nblk = (d_out + 7) / 8;
+        const int64_t nblk = opt.dense ? (d_out + 7) / 8 : 0;  // (derivative columns only: no value matrix)
         plan.dense_coef.assign((size_t)nblk * k4s * 32, 0.0);
         for (int64_t i = 0; i < K; ++i) {
             const int32_t e = nz[i].block * kBlockWidth + nz[i].lane;
@@ -618,10 +621,32 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             plan.dense_meta[2 * i + 1] = plan.ent_tab[e] > 0 ? plan.ent_tab[e] : -1 - plan.ent_dim[e];
             const int64_t k4 = i >> 2, tig = i & 3;
             const ld* src = &C[(size_t)nz[i].term * d_out];
-            for (int64_t o = 0; o < d_out; ++o)
+            for (int64_t o = 0; o < d_out && opt.dense; ++o)
                 plan.dense_coef[(size_t)(((o >> 3) * k4s + k4) * 32 + 4 * (o & 7) + tig)] = (double)src[o];
         }
-        plan.has_dense = true;
+        plan.has_dense = opt.dense;
+        if (dense_grad) {
+            const int64_t ncol = d_out * n_gd, nblk_g = (ncol + 7) / 8;
+            plan.dense_grad_coef.assign((size_t)nblk_g * k4s * 32, 0.0);
+            plan.dense_grad_c0.resize((size_t)ncol);
+            plan.dense_grad_col.resize((size_t)ncol);
+            for (int64_t c = 0; c < ncol; ++c) {
+                const int64_t o = c / n_gd, h = c % n_gd;
+                plan.dense_grad_c0[c] = (double)Cd[(size_t)h][(size_t)o];  // term 0: the constant
+                plan.dense_grad_col[c] = (int32_t)(o * d_in + plan.grad_dims[h]);
+            }
+            for (int64_t i = 0; i < K; ++i) {
+                const int64_t k4 = i >> 2, tig = i & 3;
+                for (int64_t h = 0; h < n_gd; ++h) {
+                    const ld* src = &Cd[(size_t)h][(size_t)nz[i].term * d_out];
+                    for (int64_t o = 0; o < d_out; ++o) {
+                        const int64_t c = o * n_gd + h;
+                        plan.dense_grad_coef[(size_t)(((c >> 3) * k4s + k4) * 32 + 4 * (c & 7) + tig)] = (double)src[o];
+                    }
+                }
+            }
+            plan.has_dense_grad = true;
+        }
     }
     if (!opt.sparse) {
         plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
@@ -846,6 +871,19 @@ void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, i
                 }
             }
         }
+        if (plan.has_dense_grad) {
+            const int64_t k4s = plan.dense_k4 + kDensePadK4;
+            for (int64_t c = 0; c < d_out * n_gd; ++c) {
+                double acc = 0.0;
+                for (int64_t i = 0; i < 4 * (int64_t)plan.dense_k4; ++i) {
+                    const int32_t ia = plan.dense_meta[2 * i], ib = plan.dense_meta[2 * i + 1];
+                    const double phi = tab[ia] * (ib >= 0 ? tab[ib] : xp[-1 - ib] - plan.dense_eta0[-1 - ib]);
+                    acc = std::fma(phi, plan.dense_grad_coef[(size_t)(((c >> 3) * k4s + (i >> 2)) * 32 + 4 * (c & 7) + (i & 3))], acc);
+                }
+                Jp[plan.dense_grad_col[c]] = plan.dense_grad_c0[c] + acc;
+            }
+            continue;
+        }
         for (int64_t o = 0; o < d_out; ++o)
             for (int64_t h = 0; h < n_gd; ++h) Jp[o * d_in + plan.grad_dims[h]] = tot[d_out + o * n_gd + h];
     }
@@ -872,10 +910,11 @@ struct smxh_group {
 static thread_local std::string g_plan_error;
 const char* smxh_plan_error() { return g_plan_error.c_str(); }
 
-// option bits: 1 = derivative sets, 2 = block-sparse form, 4 = dense form
+// option bits: 1 = derivative sets, 2 = block-sparse form, 4 = dense form, 8 = derivative sets as dense columns
 static smx::PlanOptions plan_options(int32_t bits) {
     smx::PlanOptions o;
     o.gradient = bits & 1, o.sparse = bits & 2, o.dense = bits & 4;
+    o.dense_gradient = (bits & 8) ? 1 : 0;
     return o;
 }
 

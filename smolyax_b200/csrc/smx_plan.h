@@ -144,12 +144,21 @@ struct FastPlan {
     std::vector<double> dense_eta0;      // (d_in) first centre of every dimension
     std::vector<double> dense_coef;      // [ceil(d_out / 8)][dense_k4 + kDensePadK4][32]: DMMA B fragments, lane = 4 * gid + tig
                                          // holds C[4 * k4 + tig][8 * jb + gid]
+
+    // Gradient in the dense form: the derivative w.r.t. a hot dimension is a polynomial over the SAME terms with mapped
+    // coefficients, i.e. more columns of the same product:  J[p][o][grad_dims[h]] = gc0[c] + sum_t Phi[p][t] G[t][c],
+    // column c = o * n_gd + h.  (Cold dimensions: row sums of the block-sparse form, as before.)
+    bool has_dense_grad = false;
+    std::vector<double> dense_grad_coef;   // [ceil(d_out n_gd / 8)][dense_k4 + kDensePadK4][32], same packing
+    std::vector<double> dense_grad_c0;     // (d_out n_gd)
+    std::vector<int32_t> dense_grad_col;   // (d_out n_gd) position of column c inside a point's (d_out, d_in) block of J
 };
 
 struct PlanOptions {
-    bool gradient = true;   // derivative coefficient sets (sparse form only)
+    bool gradient = true;   // derivative coefficient sets (block-sparse sets, or dense columns if `dense` and worthwhile)
     bool sparse = true;     // block-sparse work items (K1; values and gradients)
     bool dense = false;     // dense term matrix (K2; values, large d_out)
+    int dense_gradient = -1;  // derivative sets as dense columns: 1 yes, 0 no, -1 = when there are at least 32 of them
 };
 
 // value-table row (minus one) of hot entry h

@@ -206,10 +206,18 @@ def test_values_dense_path(case):
         assert np.array_equal(ip(x[:n]), y[:n])
     xd = torch.from_numpy(x).cuda()
     assert np.array_equal(ip(xd).cpu().numpy(), y)
-    # the gradient of a dense handle still comes from the block-sparse derivative sets
+    # gradient of a dense handle: derivative sets of the hot dimensions as columns of the same product, cold dimensions
+    # from the block-sparse row sums; against the reference and against the handle with block-sparse derivative sets
     J_ref = g["J_ref"]
-    J = ip.gradient(x[: len(J_ref)])
+    xs = x[: len(J_ref)]
+    J = ip.gradient(xs)
     assert np.array_equal(np.isnan(J), np.isnan(J_ref))
+    ok = ~np.isnan(J_ref)
+    scale = max(1.0, float(np.max(np.abs(J_ref[ok])))) if ok.any() else 1.0
+    assert np.max(np.abs(J[ok] - J_ref[ok]), initial=0.0) <= 1e-9 * scale
+    if info["n_terms"] > 1:
+        assert info["dense_grad_columns"] > 0 and sparse.device_info()["dense_grad_columns"] == 0
+    assert np.max(np.abs(J[ok] - sparse.gradient(xs)[ok]), initial=0.0) <= 1e-12 * scale
 
 
 @pytest.mark.parametrize("d_in,d_out,n_target,rule", [(10, 203, 300, "leja"), (6, 520, 120, "leja"), (8, 100, 200, "gh"),
