@@ -5,7 +5,7 @@
 namespace smx {
 
 constexpr int kDenseTile = 32;  // points per CTA
-static_assert(kDenseStageK4 == 16 && kDensePadK4 == 32, "stages of 8 or 16 k-steps, two stages of look-ahead");
+static_assert(kDenseStageK4 == 16 && kDensePadK4 == 64, "stages of 8 or 16 k-steps; look-ahead of up to 3 x 16 k-steps");
 
 struct DenseArgs {
     const double* eta;

@@ -31,20 +31,12 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-template <int NW, int NB, int PF, int CTAS>
-__global__ void __launch_bounds__(NW * 32, CTAS)
-dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __restrict__ y) {
-    static_assert(NW % PF == 0, "the register ring is indexed with the k-step inside a stage");
+// Value table of one tile of 32 points in shared memory: row 0 = 1, hot 1-D basis values, then the products of hot pairs
+// level by level (smx_plan.h).  All threads of the CTA; ends with a __syncthreads.
+template <int NW>
+__device__ __forceinline__ void build_table(const DenseArgs& a, const double* __restrict__ x, long long p0, double* tab) {
     constexpr int kThreads = NW * 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* abuf = reinterpret_cast<double*>(smem_raw);       // [2][NW][2][32 lanes][2]: A fragments of two stages
-    double* tab = abuf + 2 * NW * 128;                         // [n_tab][kTabPitch] value table
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tig = lane & 3, gid = lane >> 2;
-    const long long p0 = (long long)blockIdx.x * kDenseTile;
-
-    // ---- prologue: value table = 1 | hot basis values | products of hot pairs, level by level ---------------------------
     if (tid < kDenseTile) tab[tid] = 1.0;
     {
         const double* xrow = x + min(p0 + lane, a.N - 1) * a.ldx;
@@ -67,6 +59,22 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
         }
         __syncthreads();
     }
+}
+
+template <int NW, int NB, int PF, int CTAS>
+__global__ void __launch_bounds__(NW * 32, CTAS)
+dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __restrict__ y) {
+    static_assert(NW % PF == 0, "the register ring is indexed with the k-step inside a stage");
+    constexpr int kThreads = NW * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* abuf = reinterpret_cast<double*>(smem_raw);       // [2][NW][2][32 lanes][2]: A fragments of two stages
+    double* tab = abuf + 2 * NW * 128;                         // [n_tab][kTabPitch] value table
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tig = lane & 3, gid = lane >> 2;
+    const long long p0 = (long long)blockIdx.x * kDenseTile;
+
+    build_table<NW>(a, x, p0, tab);
 
     // ---- main loop -----------------------------------------------------------------------------------------------------
     // The host pads the term list to whole stages of 16 k-steps with zero coefficients and appends two more stages of
@@ -182,6 +190,159 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     }
 }
 
+// ---- few outputs (up to 8 blocks = 64 columns per CTA): split K over the warps -------------------------------------
+// With few output blocks there are not enough column tiles to give every warp its own, and sharing A through shared memory
+// costs a barrier per stage.  Here every warp multiplies ALL NBT output blocks of the CTA for its own k-steps
+// (warp w: k-steps w, w + NW, ..): it builds its A fragment in registers straight from the value table (no staging, no
+// barrier in the main loop), keeps 4 x NBT accumulator tiles, and streams the B fragments of the next k-step into the
+// registers the DMMAs have just consumed.  The NW partial results are added in fixed order through shared memory.
+// B fragment load that stays where it is written (volatile asm statements keep their order: the refill of a register
+// must not be hoisted above the DMMAs that still read it, or the ring needs a second set of registers)
+__device__ __forceinline__ double ldg_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int NW, int NBT, bool FULL>
+__global__ void __launch_bounds__(NW * 32, 1)
+dense_splitk_kernel(const DenseArgs a, const double* __restrict__ x, double* __restrict__ y) {
+    constexpr int kThreads = NW * 32;
+    constexpr int kCols = 8 * NBT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab = reinterpret_cast<double*>(smem_raw);  // [n_tab][kTabPitch]; afterwards [32][kCols + 2] partial sums
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tig = lane & 3, gid = lane >> 2;
+    const long long p0 = (long long)blockIdx.x * kDenseTile;
+    build_table<NW>(a, x, p0, tab);
+
+    const int jb0 = blockIdx.y * NBT;
+    const int nbv = min(NBT, a.nblk - jb0);
+    const size_t bstride = (size_t)(a.k4 + kDensePadK4) * 32;
+    const double* bbase = a.coef + lane;
+    unsigned boff[NBT];
+#pragma unroll
+    for (int j = 0; j < NBT; ++j) boff[j] = (unsigned)((size_t)min(jb0 + j, a.nblk - 1) * bstride);
+
+    const double* xt = x + p0 * a.ldx;
+    int xoff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xoff[i] = (int)(min((long long)(gid + 8 * i), a.N - 1 - p0) * a.ldx);
+    auto meta_of = [&](int g) { return __ldg(a.meta + 4 * g + tig); };  // (arrays are padded: look-ahead needs no check)
+    double xc[4] = {0.0, 0.0, 0.0, 0.0};
+    auto load_cold = [&](int2 m) {
+        if (m.y < 0) {
+            const int dim = -1 - m.y;
+            const double e0 = __ldg(a.eta0 + dim);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim) - e0;
+        }
+    };
+    auto assemble = [&](int2 m, double (&v)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i];
+            v[i] = tab[m.x * kTabPitch + gid + 8 * i] * lead;
+        }
+    };
+
+    double acc[4][NBT][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NBT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // software pipeline over this warp's k-steps g, g + NW, ..: A values one step ahead, cold x and metadata two and three
+    int g = warp;
+    double a_cur[4], a_nxt[4];
+    int2 m1 = meta_of(g);
+    load_cold(m1);
+    assemble(m1, a_cur);
+    m1 = meta_of(g + NW);
+    load_cold(m1);
+    int2 m2 = meta_of(g + 2 * NW);
+    double bq[NBT];
+#pragma unroll
+    for (int j = 0; j < NBT; ++j) bq[j] = __ldg(bbase + boff[j] + (size_t)g * 32);
+
+    for (; g < a.k4; g += NW) {
+        assemble(m1, a_nxt);                     // k-step g + NW (its cold x was loaded one iteration ago)
+        load_cold(m2);                           // k-step g + 2 NW
+        const int2 m3 = meta_of(g + 3 * NW);
+        const double* bn = bbase + (size_t)(g + NW) * 32;
+#pragma unroll
+        for (int j = 0; j < NBT; ++j) {
+            if (FULL || j < nbv) {
+                dmma(acc[0][j], a_cur[0], bq[j]);
+                dmma(acc[1][j], a_cur[1], bq[j]);
+                dmma(acc[2][j], a_cur[2], bq[j]);
+                dmma(acc[3][j], a_cur[3], bq[j]);
+            }
+            bq[j] = ldg_pinned(bn + boff[j]);    // refill the registers just consumed with the next k-step's fragment
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a_cur[i] = a_nxt[i];
+        m1 = m2;
+        m2 = m3;
+    }
+
+    // ---- add the warps' partial sums in fixed order (deterministic), then one coalesced store --------------------------
+    constexpr int kRedPitch = kCols + 2;
+    double* red = tab;
+    __syncthreads();  // the value table is dead
+#pragma unroll 1
+    for (int w = 0; w < NW; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NBT; ++j) {
+                    double2* dst = reinterpret_cast<double2*>(red + (gid + 8 * i) * kRedPitch + 8 * j + 2 * tig);
+                    double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                    if (w > 0) {
+                        const double2 old = *dst;
+                        v.x += old.x, v.y += old.y;
+                    }
+                    *dst = v;
+                }
+        }
+        __syncthreads();
+    }
+    const int ncols = (int)min((long long)kCols, a.ncol - 8ll * jb0);
+    for (int idx = tid; idx < kDenseTile * ncols; idx += kThreads) {
+        const int p = idx / ncols, c = idx - p * ncols;
+        if (p0 + p >= a.N) break;
+        const long long col = 8ll * jb0 + c;
+        y[(p0 + p) * a.ldy + (a.colmap ? __ldg(a.colmap + col) : col)] = __ldg(a.c0 + col) + red[p * kRedPitch + c];
+    }
+}
+
+size_t splitk_smem_bytes(int n_tab, int nbt) {
+    return sizeof(double) * std::max((size_t)n_tab * kTabPitch, (size_t)kDenseTile * (8 * nbt + 2));
+}
+
+template <int NW, int NBT, bool FULL>
+int launch_splitk_(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
+    const size_t smem = splitk_smem_bytes(a.n_tab, NBT);
+    static size_t opted = 0;
+    if (smem > opted) {
+        SMX_CUDA(cudaFuncSetAttribute(dense_splitk_kernel<NW, NBT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted = smem;
+    }
+    const long long tiles = (a.N + kDenseTile - 1) / kDenseTile;
+    const int groups = (a.nblk + NBT - 1) / NBT;
+    dense_splitk_kernel<NW, NBT, FULL><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
+    SMX_LAUNCH_CHECK("dense_splitk_kernel");
+    return SMX_OK;
+}
+
+template <int NW, int NBT>
+int launch_splitk(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
+    // every column group full: no per-block predicate in the inner loop
+    return a.nblk % NBT == 0 ? launch_splitk_<NW, NBT, true>(a, x, y, st) : launch_splitk_<NW, NBT, false>(a, x, y, st);
+}
+
 size_t dense_smem_bytes(int n_tab, int nw) { return sizeof(double) * ((size_t)2 * nw * 128 + (size_t)n_tab * kTabPitch); }
 
 template <int NW, int NB, int PF, int CTAS>
@@ -213,6 +374,15 @@ int dense_kernel_launch(const DenseArgs& a, const double* x, double* y, cudaStre
     int device = 0, smem_sm = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    static const int want_splitk = std::getenv("SMX_DENSE_SPLITK") ? std::atoi(std::getenv("SMX_DENSE_SPLITK")) : -1;
+    // up to 40 output blocks (320 columns): column groups of at most 8 blocks (the accumulators of 32 points x 64 columns
+    // are 128 registers per thread), K split over the warps of a CTA
+    // (measured: 0.76 vs 0.63 of the DMMA rate at 8 blocks; with two or more groups the staged kernel below wins)
+    if (want_splitk != 0 && !want_nb && (a.nblk <= 8 || want_splitk > 0)) {
+        const int groups = (a.nblk + 7) / 8, per = (a.nblk + groups - 1) / groups;
+        if (per <= 4) return launch_splitk<16, 4>(a, x, y, st);
+        return launch_splitk<8, 8>(a, x, y, st);
+    }
     const int nb = want_nb ? want_nb : (a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1);
     const int nw = want_nw ? want_nw : (nb == 4 ? 16 : 8);
     const bool two_fit = 2 * (dense_smem_bytes(a.n_tab, 8) + 1024) <= (size_t)smem_sm;

@@ -67,7 +67,7 @@ constexpr int kMaxLevels = 16;
 
 constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
 constexpr int kDenseStageK4 = 16;  // dense form: the term list is padded to whole stages of 16 k-steps (64 terms) ..
-constexpr int kDensePadK4 = 32;    // .. and every array carries two more stages of zeros (look-ahead without bounds checks)
+constexpr int kDensePadK4 = 64;    // .. and every array carries four more stages of zeros (look-ahead without bounds checks)
 constexpr int kTabPitch = 36;      // doubles per value-table row in shared memory (32 points + 32 bytes of skew:
                                    // rows r, r' with r != r' (mod 4) never share a bank in the DMMA A-fragment loads)
 
