@@ -101,6 +101,8 @@ struct FastDevice {
     int64_t bytes = 0;
     int sm_count = 148;
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
+    bool flat_ok = false;  // every row has a factor list: the kernel variant without product rows can run
+    bool flat = false;     // .. and is the one chosen (8 warps, two CTAs per SM)
 };
 int fast_upload(const FastPlan& plan, FastDevice& dev);
 void fast_free(FastDevice& dev);

@@ -105,6 +105,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
                                                              : "value table does not fit in shared memory");
         return SMX_OK;
     }
+    dev.flat_ok = plan.flat_ok;
     if ((rc = fast_kernel_prepare(dev))) return dev.has_dense ? SMX_OK : rc;
 
     std::vector<double> packed;
@@ -224,6 +225,7 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.n_levels = d.n_levels;
     a.hot_dims = d.hot_dims;
     a.n_pairs = d.n_pairs;
+    a.flat = d.flat ? 1 : 0;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
     const int rc = fast_kernel_launch(d, a, x, out, st);
     if (scratch) cudaFreeAsync(scratch, st);

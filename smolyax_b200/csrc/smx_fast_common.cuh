@@ -31,6 +31,7 @@ struct FastArgs {
     const int32_t* grad_dims;
     long long d_in;
     int n_hot, n_hot_rows, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
+    int flat;                // 1: the value table holds the hot rows only, product rows are multiplied on the fly
     int level_off[kMaxLevels + 2];
     int warp_off[kMaxWarps + 1];  // work items of warp w are [warp_off[w], warp_off[w + 1]) of the (re-ordered) directory
 };
@@ -42,6 +43,7 @@ struct alignas(16) ItemBuffer {
     int etaoff[16];   // offset of the entry's centres in `eta`
     int ridx[16];     // value-table rows, transposed: ridx[4 * k + s] = row 4 * s + k (0 beyond the item's rows)
     double eta0[16];  // first centre of each entry
+    int4 fac[16];     // row slot i (k-step i >> 2, A-fragment column i & 3) as a product of four hot rows (0 = ones row)
     double coef[kChunkRows * kBlockWidth];
 };
 static_assert(offsetof(ItemBuffer, coef) == kMetaInts * 4, "metadata record layout");

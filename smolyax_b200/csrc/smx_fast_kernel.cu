@@ -97,6 +97,16 @@ __device__ __forceinline__ void dmma_(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// D = A * B (first k-step of an item: the accumulators need no clearing)
+template <int ABL = 0>
+__device__ __forceinline__ void dmma_first(double (&c)[2], double a, double b) {
+    if (ABL == 1) {
+        c[0] = a, c[1] = b;
+        return;
+    }
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};" : "=d"(c[0]), "=d"(c[1]) : "d"(a), "d"(b), "d"(0.0));
+}
+
 // One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
 template <int ABL = 0>
 __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, int c,
@@ -111,7 +121,7 @@ __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap*
 }
 
 // ABL != 0 are timing experiments (wrong results on purpose): 1 = no DMMA, 2 = no prologue, 3 = no x tiles / basis values
-template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2>
+template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2, bool FLAT = false>
 __global__ void __launch_bounds__(NW * 32, CTAS)
 fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -121,9 +131,12 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
     ItemStage* stages = reinterpret_cast<ItemStage*>(xtiles + NW);                // [NW]
     double* tab = reinterpret_cast<double*>(stages + NW);                         // [n_tab][kTabPitch] value table
-    int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)a.n_tab * kTabPitch);     // [n_chunks] item directory
+    // FLAT: only the ones row and the hot rows; the products of hot pairs are multiplied on the fly from the factor lists
+    // of the item metadata (no product rows => a third of the table, no product pass, one barrier less, two CTAs per SM)
+    const int tab_rows = FLAT ? 1 + a.n_hot_rows : a.n_tab;
+    int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)tab_rows * kTabPitch);    // [n_chunks] item directory
     int4* s_fac = s_dir + a.n_chunks;                                             // [n_flat] hot rows of each product row
-    double* s_eta = reinterpret_cast<double*>(s_fac + a.n_flat);                  // [n_hot] centres of the hot dimensions
+    double* s_eta = reinterpret_cast<double*>(s_fac + (FLAT ? 0 : a.n_flat));     // [n_hot] centres of the hot dimensions
     int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // [n_pairs]
     int* s_hot_off = reinterpret_cast<int*>(s_pairs + a.n_pairs);                 // [hot_dims + 1]
     int* s_hot_row = s_hot_off + a.hot_dims + 1;                                  // [n_hot] value-table row of hot pair k
@@ -139,7 +152,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     for (int i = tid; i < a.n_pairs; i += kThreads) s_pairs[i] = __ldg(a.tab_pairs + i);
     for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
     for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
-    for (int i = tid; i < a.n_flat; i += kThreads) s_fac[i] = __ldg(a.tab_factors + i);
+    if (!FLAT)
+        for (int i = tid; i < a.n_flat; i += kThreads) s_fac[i] = __ldg(a.tab_factors + i);
     if (lane == 0) {
         mbar_init(&st.bar[0], 1);
         mbar_init(&st.bar[1], 1);
@@ -181,15 +195,19 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             }
         }
         __syncthreads();
-        if (ABL != 2) {
+        if (ABL != 2 && !FLAT) {
             // products of 2..4 hot pairs in one pass straight from the hot rows (row 0 = 1 pads short products) ..
-            const int flat_begin = 1 + a.n_hot_rows, count = a.n_flat * kTile;
+            // (two points per thread: rows are 16-byte aligned and the products are elementwise)
+            const int flat_begin = 1 + a.n_hot_rows, count = a.n_flat * (kTile / 2);
 #pragma unroll 4
             for (int idx = tid; idx < count; idx += kThreads) {
-                const int k = idx >> 5, s = idx & 31;
+                const int k = idx >> 4, s = (idx & 15) * 2;
                 const int4 f = s_fac[k];
-                tab[(flat_begin + k) * kTabPitch + s] = (tab[f.x * kTabPitch + s] * tab[f.y * kTabPitch + s]) *
-                                                        (tab[f.z * kTabPitch + s] * tab[f.w * kTabPitch + s]);
+                const double2 u = *reinterpret_cast<const double2*>(tab + f.x * kTabPitch + s);
+                const double2 v = *reinterpret_cast<const double2*>(tab + f.y * kTabPitch + s);
+                const double2 w = *reinterpret_cast<const double2*>(tab + f.z * kTabPitch + s);
+                const double2 z = *reinterpret_cast<const double2*>(tab + f.w * kTabPitch + s);
+                *reinterpret_cast<double2*>(tab + (flat_begin + k) * kTabPitch + s) = make_double2((u.x * v.x) * (w.x * z.x), (u.y * v.y) * (w.y * z.y));
             }
             __syncthreads();
             // .. and, only for hot parts of five and more pairs, level by level from their parents
@@ -229,13 +247,35 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
                 // fragment loads of the first two k-steps go out first: their latency overlaps the basis-value work below
                 const int4 r4 = *reinterpret_cast<const int4*>(ib.ridx + 4 * tig);  // this lane's row of every k-step
+                const int nf = (dir.z >> 8) & 7;                                    // FLAT: most hot factors of any row
+                auto load_a = [&](int s, int row, double2& lo, double2& hi) {       // A fragment of k-step s: 4 points of one row
+                    const double* q = tab + 2 * gid;
+                    if (!FLAT) {
+                        lo = *reinterpret_cast<const double2*>(q + row * kTabPitch);
+                        hi = *reinterpret_cast<const double2*>(q + row * kTabPitch + 16);
+                        return;
+                    }
+                    const int4 f = ib.fac[4 * s + tig];
+                    lo = *reinterpret_cast<const double2*>(q + f.x * kTabPitch);
+                    hi = *reinterpret_cast<const double2*>(q + f.x * kTabPitch + 16);
+                    if (nf > 1) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(q + f.y * kTabPitch);
+                        const double2 h2 = *reinterpret_cast<const double2*>(q + f.y * kTabPitch + 16);
+                        lo.x *= l2.x, lo.y *= l2.y, hi.x *= h2.x, hi.y *= h2.y;
+                    }
+                    if (nf > 2) {
+                        const double2 l3 = *reinterpret_cast<const double2*>(q + f.z * kTabPitch);
+                        const double2 h3 = *reinterpret_cast<const double2*>(q + f.z * kTabPitch + 16);
+                        const double2 l4 = *reinterpret_cast<const double2*>(q + f.w * kTabPitch);
+                        const double2 h4 = *reinterpret_cast<const double2*>(q + f.w * kTabPitch + 16);
+                        lo.x *= l3.x * l4.x, lo.y *= l3.y * l4.y, hi.x *= h3.x * h4.x, hi.y *= h3.y * h4.y;
+                    }
+                };
                 const double2 b0 = *reinterpret_cast<const double2*>(ib.coef + 2 * lane);
-                double2 b1 = make_double2(0.0, 0.0), a1lo = b1, a1hi = b1;
+                double2 b1 = make_double2(0.0, 0.0), a1lo = b1, a1hi = b1, a0lo, a0hi;
                 if (EARLY >= 2) b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
-                const double* ap0 = tab + r4.x * kTabPitch + 2 * gid;
-                const double* ap1 = tab + r4.y * kTabPitch + 2 * gid;
-                const double2 a0lo = *reinterpret_cast<const double2*>(ap0), a0hi = *reinterpret_cast<const double2*>(ap0 + 16);
-                if (EARLY >= 2) a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
+                load_a(0, r4.x, a0lo, a0hi);
+                if (EARLY >= 2) load_a(1, r4.y, a1lo, a1hi);
 
                 // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
                 double v[4][4];
@@ -264,37 +304,29 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
                 if (c + 1 < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], set, p0);
 
-                // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients)
+                // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients).
+                // Every k-step runs both n-tiles: after the degree-major ordering of the hot entries all but one or two of
+                // the (k-step, half block) pairs of a plan carry coefficients, so skipping the empty ones costs more in
+                // predicates and accumulator clearing than it saves (the first k-step writes the accumulators).
                 double acc[4][2][2];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-                const int km = dir.z >> 8;  // bit 2 s + j: k-step s touches entries of n-tile j at all
                 {
                     const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
-                    if (km & 1) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b0.x);
-                    }
-                    if (km & 2) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b0.y);
+                    for (int i = 0; i < 4; ++i) {
+                        dmma_first<ABL>(acc[i][0], af[i], b0.x);
+                        dmma_first<ABL>(acc[i][1], af[i], b0.y);
                     }
                 }
                 if (ksteps > 1) {
                     if (EARLY < 2) {
                         b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
-                        a1lo = *reinterpret_cast<const double2*>(ap1), a1hi = *reinterpret_cast<const double2*>(ap1 + 16);
+                        load_a(1, r4.y, a1lo, a1hi);
                     }
                     const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
-                    if (km & 4) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b1.x);
-                    }
-                    if (km & 8) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b1.y);
+                    for (int i = 0; i < 4; ++i) {
+                        dmma_<ABL>(acc[i][0], af[i], b1.x);
+                        dmma_<ABL>(acc[i][1], af[i], b1.y);
                     }
                 }
                 if (ksteps > 2) {
@@ -302,18 +334,14 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 #pragma unroll
                     for (int s = 2; s < 4; ++s) {
                         if (s >= ksteps) break;
-                        const double* ap = tab + rws[s - 2] * kTabPitch + 2 * gid;
-                        const double2 a01 = *reinterpret_cast<const double2*>(ap);
-                        const double2 a23 = *reinterpret_cast<const double2*>(ap + 16);
+                        double2 a01, a23;
+                        load_a(s, rws[s - 2], a01, a23);
                         const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
                         const double af[4] = {a01.x, a01.y, a23.x, a23.y};
-                        if (km & (1 << (2 * s))) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][0], af[i], b.x);
-                        }
-                        if (km & (2 << (2 * s))) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) dmma_<ABL>(acc[i][1], af[i], b.y);
+                        for (int i = 0; i < 4; ++i) {
+                            dmma_<ABL>(acc[i][0], af[i], b.x);
+                            dmma_<ABL>(acc[i][1], af[i], b.y);
                         }
                     }
                 }
@@ -370,8 +398,9 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     }
 }
 
-size_t smem_bytes(const FastDevice& d, int nw) {
-    return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + ((size_t)d.n_tab * kTabPitch + (size_t)d.n_hot) * sizeof(double) + (size_t)d.n_flat * sizeof(int4) + 16 +
+size_t smem_bytes(const FastDevice& d, int nw, bool flat = false) {
+    const size_t rows = flat ? 1 + (size_t)d.n_hot_rows : (size_t)d.n_tab;
+    return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + (rows * kTabPitch + (size_t)d.n_hot) * sizeof(double) + (flat ? 0 : (size_t)d.n_flat * sizeof(int4)) + 16 +
            (size_t)d.n_chunks * sizeof(int4) + (size_t)d.n_pairs * sizeof(int2) + ((size_t)d.hot_dims + 1 + d.n_hot) * sizeof(int) + 16;
 }
 
@@ -394,12 +423,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2>
+template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2, bool FLAT = false>
 int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * CTAS);
-    if (ABL != 0 || GRAD || EARLY != 2)
-        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW)));
-    fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY><<<(unsigned)grid, NW * 32, smem_bytes(d, NW), st>>>(map, a, x, y);
+    if (ABL != 0 || GRAD || EARLY != 2 || FLAT)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, FLAT)));
+    fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY, FLAT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, FLAT), st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_eval_kernel");
     return SMX_OK;
 }
@@ -419,6 +448,20 @@ int fast_kernel_prepare(FastDevice& d) {
     const bool fits8 = smem_bytes(d, 8) <= (size_t)smem_optin;
     const bool fits12 = smem_bytes(d, 12) <= (size_t)smem_optin;
     const bool fits16 = smem_bytes(d, 16) <= (size_t)smem_optin;
+    // preferred: no product rows in the table (two CTAs of 8 or 6 warps per SM: the barriers and the prologue of one tile
+    // overlap the main loop of another); needs a factor list for every row (hot parts of at most four pairs)
+    static const int want_flat = std::getenv("SMX_FAST_FLAT") ? std::atoi(std::getenv("SMX_FAST_FLAT")) : 1;
+    d.flat = false;
+    if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 6)) {
+        for (int nw : {8, 6}) {
+            if (want != 0 && want != nw) continue;
+            if (2 * (smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) {
+                d.flat = true;
+                d.warps = nw;
+                return SMX_OK;
+            }
+        }
+    }
     d.warps = 0;
     if (want == 16 && fits16) d.warps = 16;
     else if (want == 12 && fits12) d.warps = 12;
@@ -453,6 +496,10 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
+    if (d.flat) {
+        if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
+        return d.warps == 8 ? launch<8, 2, 0, false, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, false, 2, true>(map, a, d, x, y, st);
+    }
     if (a.gradient) {
         if (d.warps == 4) return launch<4, 2, 0, true>(map, a, d, x, y, st);
         if (d.warps == 8) return launch<8, 1, 0, true>(map, a, d, x, y, st);

@@ -757,8 +757,28 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         plan.chunk_kmask[c] = kmask;
         plan.padded_fma += 32 * __builtin_popcount((unsigned)kmask);
         int32_t* dir = &plan.chunk_dir[(size_t)c * 4];
-        dir[0] = r0, dir[1] = rows, dir[2] = plan.chunk_flags[c] | (kmask << 8), dir[3] = plan.ent_dim[e0];
         int32_t* meta = &plan.chunk_meta[(size_t)c * kMetaInts];
+        // every row slot as the product of up to four hot rows (row 0 = the ones row pads): the kernel variant without
+        // product rows in the value table multiplies them on the fly.  nf = most factors of any row of the item.
+        int32_t nf = 1;
+        const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
+        for (int32_t i = 0; i < kBlockWidth; ++i) {
+            int32_t* f4 = meta + 96 + 4 * i;
+            const int32_t row = i < rows ? plan.chunk_rows[r0 + i] : 0;
+            if (row < flat_begin) {
+                f4[0] = row;
+            } else if (row - flat_begin < n_flat) {
+                int32_t cnt = 0;
+                for (int f = 0; f < 4; ++f) {
+                    f4[f] = plan.tab_factors[(size_t)(row - flat_begin) * 4 + f];
+                    if (f4[f] != 0) cnt = f + 1;
+                }
+                nf = std::max(nf, cnt);
+            } else {
+                plan.flat_ok = false;  // a hot part of five or more pairs: only the variant with product rows can run
+            }
+        }
+        dir[0] = r0, dir[1] = rows, dir[2] = plan.chunk_flags[c] | (nf << 8), dir[3] = plan.ent_dim[e0];
         double eta0[kBlockWidth];
         for (int i = 0; i < kBlockWidth; ++i) {
             meta[i] = plan.ent_tab[e0 + i];
@@ -1003,6 +1023,16 @@ void smxh_plan_stats(void* p, int64_t* out) {
                      pl->n_levels, pl->nested ? 1 : 0, pl->n_summands, pl->w_raw, pl->w_pad};
     (void)pl->n_tab;
     std::memcpy(out, v, sizeof(v));
+}
+// per work item: rows, flags, kmask (statistics for tests and tuning); returns the number of items
+int32_t smxh_plan_items(void* p, int32_t* out, int32_t capacity) {
+    auto* pl = static_cast<smx::FastPlan*>(p);
+    for (int32_t c = 0; c < pl->n_chunks && c < capacity; ++c) {
+        out[3 * c] = pl->chunk_off[c + 1] - pl->chunk_off[c];
+        out[3 * c + 1] = pl->chunk_flags[c];
+        out[3 * c + 2] = pl->chunk_kmask[c];
+    }
+    return pl->n_chunks;
 }
 // Verification aid, CPU tests only (see smx_plan.h).
 void smxh_plan_eval_host(void* p, const double* x, int64_t N, int64_t ldx, double* y) {

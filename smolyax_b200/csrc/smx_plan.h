@@ -65,7 +65,7 @@ constexpr int kBlockWidth = 16;    // entries per block: 4 lane-groups x 4 entri
 constexpr int kChunkRows = 16;     // rows per work item
 constexpr int kMaxLevels = 16;
 
-constexpr int kMetaInts = 4 * 16 + 2 * 16;  // 384 bytes
+constexpr int kMetaInts = 4 * 16 + 2 * 16 + 4 * 16;  // 640 bytes
 constexpr int kDenseStageK4 = 16;  // dense form: the term list is padded to whole stages of 16 k-steps (64 terms) ..
 constexpr int kDensePadK4 = 64;    // .. and every array carries four more stages of zeros (look-ahead without bounds checks)
 constexpr int kTabPitch = 36;      // doubles per value-table row in shared memory (32 points + 32 bytes of skew:
@@ -123,9 +123,12 @@ struct FastPlan {
     std::vector<int32_t> nan_off;
     std::vector<double> nan_nodes;
     // the same information packed for the kernel: one directory entry and one metadata record per work item
-    std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags | kmask << 8, first column of x
+    std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags | nf << 8 (nf = most hot
+                                         // factors of any of its rows), first column of x
+    bool flat_ok = true;                 // every row is a product of at most four hot rows (factor lists in the metadata)
     std::vector<int32_t> chunk_kmask;    // bit 2 s + j set: k-step s has a non-zero coefficient in entries 8 j .. 8 j + 7
-    std::vector<int32_t> chunk_meta;     // kMetaInts ints per item: tab[16], deg[16], eta offset[16], row index[16], eta0[16] (doubles)
+    std::vector<int32_t> chunk_meta;     // kMetaInts ints per item: tab[16], deg[16], eta offset[16], row index[16], eta0[16]
+                                         // (doubles), then per row slot the four hot rows whose product it is (int4)
     std::vector<int32_t> hot_off;        // prefix sums of the degrees of the hot dimensions, size hot_dims + 1
     std::vector<int32_t> hot_pos;        // entry index of hot pair (d, a), indexed hot_off[d] + a - 1 (hot entries are
                                          // stored degree-major: blocks of equal degree share most of their rows)
