@@ -37,6 +37,7 @@ struct FastArgs {
 };
 
 // One work item as the kernel sees it in shared memory: metadata record (smx_plan.h, kMetaInts) + packed coefficients.
+// Device copy: every value-table row index (tab, ridx, fac) is pre-multiplied by kTabPitch (offset in doubles).
 struct alignas(16) ItemBuffer {
     int tab[16];      // value-table row of each entry (hot blocks)
     int deg[16];      // degree of each entry (0: dummy)

@@ -246,28 +246,29 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
 
                 // fragment loads of the first two k-steps go out first: their latency overlaps the basis-value work below
+                // (table rows in the device copy of the metadata are offsets in doubles: row * kTabPitch)
                 const int4 r4 = *reinterpret_cast<const int4*>(ib.ridx + 4 * tig);  // this lane's row of every k-step
                 const int nf = (dir.z >> 8) & 7;                                    // FLAT: most hot factors of any row
                 auto load_a = [&](int s, int row, double2& lo, double2& hi) {       // A fragment of k-step s: 4 points of one row
                     const double* q = tab + 2 * gid;
                     if (!FLAT) {
-                        lo = *reinterpret_cast<const double2*>(q + row * kTabPitch);
-                        hi = *reinterpret_cast<const double2*>(q + row * kTabPitch + 16);
+                        lo = *reinterpret_cast<const double2*>(q + row);
+                        hi = *reinterpret_cast<const double2*>(q + row + 16);
                         return;
                     }
                     const int4 f = ib.fac[4 * s + tig];
-                    lo = *reinterpret_cast<const double2*>(q + f.x * kTabPitch);
-                    hi = *reinterpret_cast<const double2*>(q + f.x * kTabPitch + 16);
+                    lo = *reinterpret_cast<const double2*>(q + f.x);
+                    hi = *reinterpret_cast<const double2*>(q + f.x + 16);
                     if (nf > 1) {
-                        const double2 l2 = *reinterpret_cast<const double2*>(q + f.y * kTabPitch);
-                        const double2 h2 = *reinterpret_cast<const double2*>(q + f.y * kTabPitch + 16);
+                        const double2 l2 = *reinterpret_cast<const double2*>(q + f.y);
+                        const double2 h2 = *reinterpret_cast<const double2*>(q + f.y + 16);
                         lo.x *= l2.x, lo.y *= l2.y, hi.x *= h2.x, hi.y *= h2.y;
                     }
                     if (nf > 2) {
-                        const double2 l3 = *reinterpret_cast<const double2*>(q + f.z * kTabPitch);
-                        const double2 h3 = *reinterpret_cast<const double2*>(q + f.z * kTabPitch + 16);
-                        const double2 l4 = *reinterpret_cast<const double2*>(q + f.w * kTabPitch);
-                        const double2 h4 = *reinterpret_cast<const double2*>(q + f.w * kTabPitch + 16);
+                        const double2 l3 = *reinterpret_cast<const double2*>(q + f.z);
+                        const double2 h3 = *reinterpret_cast<const double2*>(q + f.z + 16);
+                        const double2 l4 = *reinterpret_cast<const double2*>(q + f.w);
+                        const double2 h4 = *reinterpret_cast<const double2*>(q + f.w + 16);
                         lo.x *= l3.x * l4.x, lo.y *= l3.y * l4.y, hi.x *= h3.x * h4.x, hi.y *= h3.y * h4.y;
                     }
                 };
@@ -284,7 +285,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const int tabs[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const double* tr = tab + tabs[e] * kTabPitch + 2 * gid;
+                        const double* tr = tab + tabs[e] + 2 * gid;
                         const double2 lo = *reinterpret_cast<const double2*>(tr);
                         const double2 hi = *reinterpret_cast<const double2*>(tr + 16);
                         v[0][e] = lo.x, v[1][e] = lo.y, v[2][e] = hi.x, v[3][e] = hi.y;
@@ -298,7 +299,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         const double* xr = xs + (gid + 8 * i) * kBlockWidth;
                         const double2 lo = *reinterpret_cast<const double2*>(xr + (((2 * tig) ^ gid) << 1));
                         const double2 hi = *reinterpret_cast<const double2*>(xr + (((2 * tig + 1) ^ gid) << 1));
-                        v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
+                        if (dir.z & kChunkEtaZero) v[i][0] = lo.x, v[i][1] = lo.y, v[i][2] = hi.x, v[i][3] = hi.y;  // pi = x
+                        else v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free

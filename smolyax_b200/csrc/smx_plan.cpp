@@ -778,6 +778,9 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                 plan.flat_ok = false;  // a hot part of five or more pairs: only the variant with product rows can run
             }
         }
+        bool eta_zero = !(plan.chunk_flags[c] & kChunkHot);
+        for (int i = 0; i < kBlockWidth; ++i) eta_zero = eta_zero && plan.ent_eta0[e0 + i] == 0.0;
+        if (eta_zero) plan.chunk_flags[c] |= kChunkEtaZero;
         dir[0] = r0, dir[1] = rows, dir[2] = plan.chunk_flags[c] | (nf << 8), dir[3] = plan.ent_dim[e0];
         double eta0[kBlockWidth];
         for (int i = 0; i < kBlockWidth; ++i) {

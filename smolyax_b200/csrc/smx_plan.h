@@ -76,6 +76,7 @@ constexpr int kChunkHot = 1;      // all 16 entries are hot: their basis values 
 constexpr int kChunkContig = 2;   // 16 degree-1 entries on consecutive columns of x starting at an even column
 constexpr int kChunkInside = 4;   // .. and the 16 columns all exist (first column + 16 <= d_in)
 constexpr int kChunkSplit = 8;    // the block's rows are spread over more than one item
+constexpr int kChunkEtaZero = 16; // cold block whose first centres are all zero (default Leja domain): pi = x
 
 struct FastPlan {
     int64_t d_in = 0, d_out = 0;
