@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "smx_dense.cuh"
 #include "smx_fast_common.cuh"
@@ -152,9 +153,30 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         for (int w = nw; w <= kMaxWarps; ++w) dev.warp_off[w] = (int32_t)pos;
     }
     if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
+    // One record per (work item, coefficient set): metadata (640 B) followed by the set's packed coefficients, so that the
+    // kernel stages an item with ONE bulk copy.  dir[0] = offset of the item's first record in units of 128 bytes; the
+    // records of the other sets follow at a stride of 5 + 4 * ksteps units.
+    {
+        std::vector<double> records;
+        const size_t nsets = (size_t)plan.n_sets;
+        size_t units = 0;
+        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) units += nsets * (5 + 4 * (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4));
+        if (units >= (size_t)INT32_MAX) return fail(SMX_ERR_UNSUPPORTED, "too many coefficient sets for the block-sparse form");
+        records.assign(units * 16, 0.0);
+        size_t at = 0;
+        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) {
+            const size_t ksteps = (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4), k0 = (size_t)dir[(size_t)pos * 4];
+            dir[(size_t)pos * 4] = (int32_t)at;
+            for (size_t o = 0; o < nsets; ++o) {
+                std::memcpy(&records[at * 16], &meta[(size_t)pos * kMetaInts], kMetaInts * 4);
+                std::memcpy(&records[(at + 5) * 16], &packed[(k0 + o * ksteps) * kKStepDoubles], ksteps * kKStepDoubles * 8);
+                at += 5 + 4 * ksteps;
+            }
+        }
+        std::vector<double>().swap(packed);
+        if ((rc = upload(records, &dev.coef, dev.bytes, 2))) return rc;
+    }
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
-    if ((rc = upload(meta, &dev.chunk_meta, dev.bytes, 4))) return rc;
-    if ((rc = upload(packed, &dev.coef, dev.bytes, 2))) return rc;
     dev.n_sets = plan.n_sets;
     dev.n_gd = (int32_t)plan.grad_dims.size();
     dev.grad_ok = dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
@@ -209,7 +231,6 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.hot_off = d.hot_off;
     a.hot_pos = d.hot_pos;
     a.chunk_dir = reinterpret_cast<const int4*>(d.chunk_dir);
-    a.chunk_meta = d.chunk_meta;
     a.coef = d.coef;
     a.c0 = d.c0;
     a.N = N;

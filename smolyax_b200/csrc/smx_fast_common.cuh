@@ -19,9 +19,9 @@ struct FastArgs {
     int n_flat;              // number of those rows (they come first among the product rows)
     const int32_t* hot_off;
     const int32_t* hot_pos;  // entry index of hot pair k (dimension-major numbering, = index of its centre in eta)
-    const int4* chunk_dir;   // per work item: first k-step of its packed coefficients, rows, flags, first column of x
-    const int32_t* chunk_meta;
-    const double* coef;      // packed in DMMA B-fragment order, see pack_coefficients()
+    const int4* chunk_dir;   // per work item: offset of its first record (128-byte units), rows, flags, first column of x
+    const double* coef;      // records: per (item, set) the metadata followed by the coefficients packed in DMMA
+                             // B-fragment order (pack_coefficients(), fast_upload())
     const double* c0;
     long long N, ldx, d_out, num_tiles;
     // gradient mode: y is J (N, d_out, d_in); pass q of output o is the function itself (q = 0: stores the row sums of the

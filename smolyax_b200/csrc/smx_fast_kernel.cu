@@ -115,8 +115,8 @@ __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap*
     const unsigned coef_bytes = (unsigned)ksteps * kKStepDoubles * 8;
     const bool cold = ABL == 3 ? false : !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
-    bulk_copy(&st.item[buf], a.chunk_meta + (size_t)c * kMetaInts, kMetaInts * 4, &st.bar[buf]);
-    bulk_copy(st.item[buf].coef, a.coef + ((size_t)dir.x + (size_t)o * ksteps) * kKStepDoubles, coef_bytes, &st.bar[buf]);  // o = set
+    // metadata + coefficients of (item, set o) are one contiguous record: a single bulk copy
+    bulk_copy(&st.item[buf], a.coef + ((size_t)dir.x + (size_t)o * (5 + 4 * ksteps)) * 16, kMetaInts * 4 + coef_bytes, &st.bar[buf]);
     if (cold) tma_load_2d(xs, xmap, dir.w, (int)p0, &st.bar[buf]);
 }
 
