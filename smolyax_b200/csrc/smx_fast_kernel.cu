@@ -145,6 +145,9 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     const int tig = lane & 3, gid = lane >> 2;
     ItemStage& st = stages[warp];
     double* xs = xtiles[warp].v;
+    // this lane's two 16-byte pieces of row gid of the swizzled x tile (rows gid + 8 i are 8 * 128 bytes further on)
+    const double* xlo = xs + gid * kBlockWidth + (((2 * tig) ^ gid) << 1);
+    const double* xhi = xs + gid * kBlockWidth + (((2 * tig + 1) ^ gid) << 1);
 
     // ---- once per CTA: small tables to shared memory, mbarriers --------------------------------------------------------
     for (int i = tid; i < a.n_chunks; i += kThreads) s_dir[i] = __ldg(a.chunk_dir + i);
@@ -296,9 +299,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const double* xr = xs + (gid + 8 * i) * kBlockWidth;
-                        const double2 lo = *reinterpret_cast<const double2*>(xr + (((2 * tig) ^ gid) << 1));
-                        const double2 hi = *reinterpret_cast<const double2*>(xr + (((2 * tig + 1) ^ gid) << 1));
+                        const double2 lo = *reinterpret_cast<const double2*>(xlo + i * (8 * kBlockWidth));
+                        const double2 hi = *reinterpret_cast<const double2*>(xhi + i * (8 * kBlockWidth));
                         if (dir.z & kChunkEtaZero) v[i][0] = lo.x, v[i][1] = lo.y, v[i][2] = hi.x, v[i][3] = hi.y;  // pi = x
                         else v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
                     }
