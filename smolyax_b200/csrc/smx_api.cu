@@ -353,8 +353,10 @@ int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, d
     std::lock_guard<std::mutex> lock(h->host_mutex);
     SMX_CUDA(cudaSetDevice(h->device));
     if (chunk_points <= 0) {
-        // ~64 MiB of x per stage keeps the copy engines and the SMs busy at the same time
-        chunk_points = std::max<int64_t>(1024, (64ll << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
+        // ~32 MiB per stage keeps the copy engines and the SMs busy at the same time (measured 8 .. 1024 MiB: 149 .. 175 ms
+        // per 8 GB at cfg2, i.e. the PCIe link - 54 GB/s - whatever the chunk)
+        static const long long chunk_mb = std::getenv("SMX_HOST_CHUNK_MB") ? std::atoll(std::getenv("SMX_HOST_CHUNK_MB")) : 32;
+        chunk_points = std::max<int64_t>(1024, (chunk_mb << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
     }
     chunk_points = std::min(chunk_points, N);
     int rc;
@@ -365,8 +367,11 @@ int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, d
         const int64_t n = std::min(chunk_points, N - done);
         cudaStream_t st = h->streams[s];
         // stream order protects the stage buffers: the next use of stage s is queued behind this one
-        SMX_CUDA(cudaMemcpy2DAsync(h->stage_x[s], sizeof(double) * h->d_in, x_host + done * ldx, sizeof(double) * ldx,
-                                   sizeof(double) * h->d_in, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (ldx == h->d_in)  // contiguous rows: one linear copy
+            SMX_CUDA(cudaMemcpyAsync(h->stage_x[s], x_host + done * ldx, sizeof(double) * (size_t)n * h->d_in, cudaMemcpyHostToDevice, st));
+        else
+            SMX_CUDA(cudaMemcpy2DAsync(h->stage_x[s], sizeof(double) * h->d_in, x_host + done * ldx, sizeof(double) * ldx,
+                                       sizeof(double) * h->d_in, (size_t)n, cudaMemcpyHostToDevice, st));
         if ((rc = smx_eval(h, h->stage_x[s], n, h->d_in, h->stage_y[s], st))) return rc;
         SMX_CUDA(cudaMemcpyAsync(y_host + done * h->d_out, h->stage_y[s], sizeof(double) * (size_t)n * h->d_out,
                                  cudaMemcpyDeviceToHost, st));

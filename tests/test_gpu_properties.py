@@ -182,3 +182,69 @@ def test_headline_config_full_size_consistency():
     f_true = wl.target()(xh[sample]).reshape(-1, 1)
     assert np.max(np.abs(yd.cpu().numpy()[sample] - y_orc)) < 1e-9  # the oracle's own noise is ~1e-11 here
     assert np.max(np.abs(y_orc - f_true)) < 1e-2  # and both approximate f
+
+
+def test_dense_path_strided_unaligned_streams_and_empty_batch():
+    """GEMM-regime kernels through the C ABI directly: padded / odd / unaligned row pitches of x, an unaligned y, an
+    empty batch, two streams at once on one handle, one launch per call."""
+    from smolyax_b200 import _lib
+
+    wl = workloads.Workload("t", "leja", 37, 75, 600, 0)  # 75 outputs: odd count, partial last block, staged kernel
+    ip = _interp(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=75, f=wl.target(), batched_f=True)
+    assert ip.device_info()["has_dense_path"] == 1
+    x = wl.points(333, seed=11)
+    y = ip(x)
+    lib, h = _lib.lib, ip._handle
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for pitch, shift in ((48, 0), (49, 0), (48, 1), (37, 1)):
+        buf = torch.zeros(333 * pitch + shift, dtype=torch.float64, device="cuda")[shift:].view(333, pitch)
+        buf[:, :37] = torch.from_numpy(x).cuda()
+        out = torch.zeros(333 * 75 + 1, dtype=torch.float64, device="cuda")
+        for off in (0, 1):  # y 16-byte aligned or not
+            o = out[off:off + 333 * 75].view(333, 75)
+            _lib.check(lib.smx_eval(h, buf.data_ptr(), 333, pitch, o.data_ptr(), stream))
+            assert np.array_equal(o.cpu().numpy(), y), (pitch, shift, off)
+    assert lib.smx_eval(h, 0, 0, 37, 0, stream) == 0  # N = 0: nothing to do, no buffers needed
+    assert ip(np.zeros((0, 37))).shape == (0, 75)
+    # two streams, same handle (tables are read-only after create)
+    xd = torch.from_numpy(x).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        y1 = ip(xd)
+    with torch.cuda.stream(s2):
+        y2 = ip(xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(y1.cpu().numpy(), y) and np.array_equal(y2.cpu().numpy(), y)
+    before = lib.smx_launch_count()
+    ip(xd)
+    assert lib.smx_launch_count() == before + 1
+
+
+def test_compact_create_rejects_malformed_descriptors_and_flags():
+    from smolyax_b200 import _lib
+
+    wl = workloads.Workload("t", "gh", 6, 3, 80, 0)  # non-nested rule through the compact entry
+    ip = _interp(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=3, f=wl.target(), layout="compact")
+    ref = _interp(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=3, f=wl.target(), layout="reference")
+    x = wl.points(65, seed=2)
+    assert np.array_equal(ip(x), ref(x))
+    np.testing.assert_allclose(ip.integral(), ref.integral(), rtol=1e-12, atol=1e-13)
+    good = ip._layout
+    for key, bad in (("val_index", good["val_index"] + good["values"].shape[0]),       # row out of range
+                     ("dims", np.where(good["dims"] == good["dims"].max(), 6, good["dims"])),  # dimension out of range
+                     ("val_off", good["val_off"] + 1),                                 # shape mismatch
+                     ("degs", np.zeros_like(good["degs"]))):                           # degree 0 is not an active slot
+        layout = dict(good)
+        layout[key] = bad
+        with pytest.raises(AssertionError):
+            _lib.create_compact(layout, 6, 3, 0)
+    no_quad = dict(good)
+    no_quad["quad_pool"] = None
+    h = _lib.create_compact(no_quad, 6, 3, 0)
+    q = torch.empty(3, dtype=torch.float64, device="cuda")
+    assert _lib.lib.smx_integral(h, q.data_ptr(), None) == 1  # created without quadrature weights
+    _lib.lib.smx_destroy(h)
+    # SMX_NO_DENSE_PATH / SMX_DENSE_PATH are honoured
+    assert _lib.info(_lib.create_compact(good, 6, 3, _lib.SMX_DENSE_PATH))["has_dense_path"] == 1
+    assert _lib.info(_lib.create_compact(good, 6, 3, _lib.SMX_NO_DENSE_PATH))["has_dense_path"] == 0
