@@ -1,5 +1,7 @@
 // Definitions shared by the host side (smx_fast.cu: upload, launch) and the kernel (smx_fast_kernel.cu) of the fast path.
 #pragma once
+#include <cuda.h>
+
 #include <cstddef>
 
 #include "smx_common.cuh"
@@ -50,6 +52,9 @@ struct alignas(16) ItemBuffer {
 static_assert(offsetof(ItemBuffer, coef) == kMetaInts * 4, "metadata record layout");
 
 int fast_kernel_prepare(FastDevice& d);
+// few outputs (2 <= d_out < 32): several coefficient sets per pass (smx_fast_multi.cu)
+bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* warps);
+int multi_kernel_launch(const CUtensorMap& map, const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);
 int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);
 
 }  // namespace smx

@@ -29,83 +29,15 @@
 
 #include <cstdlib>
 
-#include "smx_fast_common.cuh"
+#include "smx_fast_device.cuh"
 
 namespace smx {
 namespace {
 
-constexpr int kXTileBytes = kTile * kBlockWidth * 8;  // 4096
-constexpr int kHotRegs = 8;                           // hot coordinates per lane kept in registers for the next tile
-
-// Per-warp staging: the x tile (TMA destination, 128-byte swizzle => 1024-byte alignment; consumed into registers at
-// the start of the item, so one buffer is enough), two item buffers, and one mbarrier per item buffer (the x tile
-// travels with its item).
-struct alignas(1024) XTile {
-    double v[kTile * kBlockWidth];
-};
 struct alignas(16) ItemStage {
     ItemBuffer item[2];
     unsigned long long bar[2];
 };
-
-// tile point t = gid + 8 * i  ->  position inside a value-table row: points (gid, gid + 8) and (gid + 16, gid + 24)
-// are adjacent pairs, the second pair 16 doubles after the first (two LDS.128 fetch a lane's four A-fragment values)
-__device__ __forceinline__ int t_slot(int t) { return ((t >> 4) & 1) * 16 + (t & 7) * 2 + ((t >> 3) & 1); }
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned addr = smem_u32(bar);
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
-// D (8x8, fp64) += A (8x4, row) * B (4x8, col): one value of A and B per lane, two of D
-template <int ABL = 0>
-__device__ __forceinline__ void dmma_(double (&c)[2], double a, double b) {
-    if (ABL == 1) {  // keep the data dependence, stay off the FP64 pipe
-        c[0] = __longlong_as_double(__double_as_longlong(c[0]) ^ __double_as_longlong(a));
-        c[1] = __longlong_as_double(__double_as_longlong(c[1]) ^ __double_as_longlong(b));
-        return;
-    }
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
-
-// D = A * B (first k-step of an item: the accumulators need no clearing)
-template <int ABL = 0>
-__device__ __forceinline__ void dmma_first(double (&c)[2], double a, double b) {
-    if (ABL == 1) {
-        c[0] = a, c[1] = b;
-        return;
-    }
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};" : "=d"(c[0]), "=d"(c[1]) : "d"(a), "d"(b), "d"(0.0));
-}
 
 // One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
 template <int ABL = 0>
@@ -456,6 +388,16 @@ int fast_kernel_prepare(FastDevice& d) {
     // overlap the main loop of another); needs a factor list for every row (hot parts of at most four pairs)
     static const int want_flat = std::getenv("SMX_FAST_FLAT") ? std::atoi(std::getenv("SMX_FAST_FLAT")) : 1;
     d.flat = false;
+    d.multi = 0;
+    {   // a few outputs: several coefficient sets per pass (its warp count also fixes the per-warp item lists)
+        int sets = 0, warps = 0;
+        if (want_flat && want == 0 && multi_kernel_shape(d, smem_optin, &sets, &warps)) {
+            d.flat = true;
+            d.multi = sets;
+            d.warps = warps;
+            return SMX_OK;
+        }
+    }
     if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 6)) {
         for (int nw : {8, 6}) {
             if (want != 0 && want != nw) continue;
@@ -500,7 +442,9 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
+    if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
     if (d.flat) {
+        if (a.gradient && d.warps == 12) return launch<12, 1, 0, true, 2, true>(map, a, d, x, y, st);
         if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
         return d.warps == 8 ? launch<8, 2, 0, false, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, false, 2, true>(map, a, d, x, y, st);
     }

@@ -272,3 +272,31 @@ def test_compact_layout_handle(case):
     err_new = np.max(np.abs((ip.integral() - Q_ld).astype(float)))
     err_ref = np.max(np.abs((g["Q_ref"] - Q_ld).astype(float)))
     assert err_new <= max(err_ref, 1e-13 * max(1.0, float(np.max(np.abs(g["Q_ref"])))))
+
+
+@pytest.mark.parametrize("d_in,d_out,n_target,rule", [(9, 2, 250, "leja"), (12, 4, 300, "leja"), (7, 5, 200, "gh"), (30, 6, 500, "leja")])
+def test_few_outputs_multi_set_kernel(d_in, d_out, n_target, rule):
+    """2..6 outputs run the block-sparse kernel with several coefficient sets per pass (smx_fast_multi.cu): against the
+    CPU oracle, ragged batch sizes, and column by column against single-output handles of the same targets."""
+    from oracle import oracle
+    from smolyax_b200 import workloads
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    w = workloads.Workload("few", rule, d_in, d_out, n_target, 0)
+    fam = w.target()
+    ip = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=fam)
+    assert ip.device_info()["has_dense_path"] == 0
+    x = w.points(205, seed=9)
+    y = ip(x)
+    y_orc = oracle.evaluate(ip.reference_layout(), x)
+    scale = max(1.0, float(np.max(np.abs(y_orc))))
+    assert np.max(np.abs(y - y_orc)) <= 5e-11 * scale  # (the oracle carries the reference's Sigma|zeta| rounding noise)
+    for n in (1, 31, 33, 64):
+        assert np.array_equal(ip(x[:n]), y[:n])
+    for o in (0, d_out - 1):
+        one = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=1, f=lambda z, o=o: fam(z)[..., o])
+        assert np.max(np.abs(one(x)[:, 0] - y[:, o])) <= 1e-13 * scale
+    J = ip.gradient(x[:16])
+    J_orc = oracle.gradient(ip.reference_layout(), x[:16])
+    ok = ~np.isnan(J_orc)
+    assert np.array_equal(np.isnan(J), np.isnan(J_orc)) and np.max(np.abs(J[ok] - J_orc[ok])) <= 1e-9 * max(1.0, float(np.max(np.abs(J_orc[ok]))))
