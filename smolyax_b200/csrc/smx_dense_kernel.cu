@@ -133,7 +133,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
     for (int u = 0; u < PF; ++u)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) bq[u][j] = __ldg(bbase + boff[j] + u * 32);
+        for (int j = 0; j < NB; ++j) bq[u][j] = j < nbv ? __ldg(bbase + boff[j] + u * 32) : 0.0;
 
     auto stage_mma = [&](int s, auto full) {
         const double2* af = reinterpret_cast<const double2*>(abuf + (s & 1) * NW * 128) + lane;
@@ -149,8 +149,10 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
                     dmma(acc[2][j], a23.x, bq[kk % PF][j]);
                     dmma(acc[3][j], a23.y, bq[kk % PF][j]);
                 }
-                // refill the slot just consumed: the fragment of k-step kk + PF (no second register set needed)
-                bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
+                // refill the slot just consumed: the fragment of k-step kk + PF (no second register set needed).  Only the
+                // blocks this warp really has: the kernel runs at the L2 -> SM bandwidth limit (64 bytes of B per DMMA),
+                // a duplicate load of a clamped block costs as much as a useful one
+                if (decltype(full)::value || j < nbv) bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
             }
         }
     };
@@ -188,160 +190,6 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
             }
         }
     }
-}
-
-// ---- 9 .. 47 output blocks: the staged kernel with the work dealt out in HALF blocks ---------------------------------
-// A warp is pinned to one SM sub-partition (warp % 4) and the FP64 pipe of a sub-partition is the bottleneck, so a stage
-// lasts as long as the most loaded sub-partition.  Whole blocks are too coarse for that: 13 blocks on 8 warps put 4 of 13
-// on one sub-partition (81 % at best; measured: 13 blocks take exactly as long as 16).  Here the unit of work is half an
-// output block - 2 of the 4 point blocks of the tile x 8 outputs, 2 DMMAs per k-step - and warp w takes the contiguous
-// range of units [w H / NW ..): 26 units on 8 warps are 4,4,3,3,3,3,3,3, i.e. 7,7,6,6 per sub-partition (93 %).
-// A range of at most 4 units touches at most 3 output blocks, so the B ring has 3 slots per k-step.
-template <int NW, int PF, int CTAS>
-__global__ void __launch_bounds__(NW * 32, CTAS)
-dense_unit_kernel(const DenseArgs a, const double* __restrict__ x, double* __restrict__ y) {
-    static_assert(NW % PF == 0, "the register ring is indexed with the k-step inside a stage");
-    constexpr int NU = 4, NBS = 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* abuf = reinterpret_cast<double*>(smem_raw);
-    double* tab = abuf + 2 * NW * 128;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tig = lane & 3, gid = lane >> 2;
-    const long long p0 = (long long)blockIdx.x * kDenseTile;
-    build_table<NW>(a, x, p0, tab);
-
-    const int n_stage = a.k4 / NW;
-    // this CTA's group of output blocks, dealt out in half blocks
-    const int gsz = (a.nblk + (int)gridDim.y - 1) / (int)gridDim.y;
-    const int g0 = blockIdx.y * gsz, gcnt = min(gsz, a.nblk - g0), H = 2 * gcnt;
-    const int t0 = warp * (H / NW) + min(warp, H % NW);        // first unit of this warp
-    const int nu = H / NW + (warp < H % NW ? 1 : 0);            // its number of units (<= NU)
-    const int jb0 = g0 + (t0 >> 1), par = t0 & 1;               // first block, and which half of it the first unit is
-    const size_t bstride = (size_t)(a.k4 + kDensePadK4) * 32;
-    const double* bbase = a.coef + lane;
-    unsigned boff[NBS];
-#pragma unroll
-    for (int j = 0; j < NBS; ++j) boff[j] = (unsigned)((size_t)min(jb0 + j, a.nblk - 1) * bstride);
-
-    const double* xt = x + p0 * a.ldx;
-    int xoff[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xoff[i] = (int)(min((long long)(gid + 8 * i), a.N - 1 - p0) * a.ldx);
-    auto meta_of = [&](int stage) { return __ldg(a.meta + 4 * (stage * NW + warp) + tig); };
-    double xc[4] = {0.0, 0.0, 0.0, 0.0};
-    auto load_cold = [&](int2 m) {
-        if (m.y < 0) {
-            const int dim = -1 - m.y;
-            const double e0 = __ldg(a.eta0 + dim);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim) - e0;
-        }
-    };
-    auto assemble = [&](int2 m, int buf) {
-        double v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i];
-            v[i] = tab[m.x * kTabPitch + gid + 8 * i] * lead;
-        }
-        double2* dst = reinterpret_cast<double2*>(abuf + (buf * NW + warp) * 128) + lane;
-        dst[0] = make_double2(v[0], v[1]);
-        dst[32] = make_double2(v[2], v[3]);
-    };
-
-    int2 m1 = meta_of(0);
-    load_cold(m1);
-    assemble(m1, 0);
-    m1 = meta_of(1);
-    __syncthreads();
-
-    double acc[NU][2][2];  // unit u: point blocks 2 h + {0, 1} of output block jb0 + ((par + u) >> 1), h = (par + u) & 1
-#pragma unroll
-    for (int u = 0; u < NU; ++u) acc[u][0][0] = acc[u][0][1] = acc[u][1][0] = acc[u][1][1] = 0.0;
-    double bq[PF][NBS];
-#pragma unroll
-    for (int r = 0; r < PF; ++r)
-#pragma unroll
-        for (int j = 0; j < NBS; ++j) bq[r][j] = __ldg(bbase + boff[j] + r * 32);
-
-    // par is warp-uniform: two copies of the stage body, each with the halves and B slots of its units fixed at compile time
-    auto stage_mma = [&](int s, auto parity) {
-        constexpr int P = decltype(parity)::value;
-        const double2* af = reinterpret_cast<const double2*>(abuf + (s & 1) * NW * 128) + lane;
-        const double* bp = bbase + (size_t)s * NW * 32;
-#pragma unroll
-        for (int kk = 0; kk < NW; ++kk) {
-            const double2 a01 = af[kk * 64], a23 = af[kk * 64 + 32];
-#pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                if (u < nu) {
-                    const double b = bq[kk % PF][(P + u) >> 1];
-                    if ((P + u) & 1) {
-                        dmma(acc[u][0], a23.x, b);
-                        dmma(acc[u][1], a23.y, b);
-                    } else {
-                        dmma(acc[u][0], a01.x, b);
-                        dmma(acc[u][1], a01.y, b);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NBS; ++j) bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
-        }
-    };
-
-    for (int s = 0; s < n_stage; ++s) {
-        const int2 m2 = meta_of(s + 2);
-        load_cold(m1);
-        if (nu > 0) {
-            if (par) stage_mma(s, std::integral_constant<int, 1>());
-            else stage_mma(s, std::integral_constant<int, 0>());
-        }
-        assemble(m1, (s + 1) & 1);
-        m1 = m2;
-        __syncthreads();
-    }
-
-    // ---- epilogue: unit u holds rows 8 (2 h + mi) + gid, columns 8 j + 2 tig + {0, 1} ------------------------------------
-    const bool vec = a.colmap == nullptr && (a.ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-        if (u >= nu) break;
-        const int h = (par + u) & 1;
-        const long long col = 8ll * (jb0 + ((par + u) >> 1)) + 2 * tig;
-        if (col >= a.ncol) continue;
-        const bool two = col + 1 < a.ncol;
-        const double c0a = __ldg(a.c0 + col), c0b = two ? __ldg(a.c0 + col + 1) : 0.0;
-        const long long ya = a.colmap ? __ldg(a.colmap + col) : col, yb = a.colmap && two ? __ldg(a.colmap + col + 1) : col + 1;
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi) {
-            const long long p = p0 + gid + 8 * (2 * h + mi);
-            if (p >= a.N) continue;
-            double* dst = y + p * a.ldy;
-            if (vec) {
-                *reinterpret_cast<double2*>(dst + ya) = make_double2(c0a + acc[u][mi][0], c0b + acc[u][mi][1]);
-            } else {
-                dst[ya] = c0a + acc[u][mi][0];
-                if (two) dst[yb] = c0b + acc[u][mi][1];
-            }
-        }
-    }
-}
-
-template <int NW, int PF, int CTAS>
-int launch_unit(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
-    const size_t smem = sizeof(double) * ((size_t)2 * NW * 128 + (size_t)a.n_tab * kTabPitch);
-    static size_t opted = 0;
-    if (smem > opted) {
-        SMX_CUDA(cudaFuncSetAttribute(dense_unit_kernel<NW, PF, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted = smem;
-    }
-    const long long tiles = (a.N + kDenseTile - 1) / kDenseTile;
-    const int groups = (a.nblk + 2 * NW - 1) / (2 * NW);  // at most 2 NW blocks (4 NW half blocks) per CTA
-    dense_unit_kernel<NW, PF, CTAS><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
-    SMX_LAUNCH_CHECK("dense_unit_kernel");
-    return SMX_OK;
 }
 
 // ---- few outputs (up to 8 blocks = 64 columns per CTA): split K over the warps -------------------------------------
@@ -433,7 +281,7 @@ dense_splitk_kernel(const DenseArgs a, const double* __restrict__ x, double* __r
                 dmma(acc[2][j], a_cur[2], bq[j]);
                 dmma(acc[3][j], a_cur[3], bq[j]);
             }
-            bq[j] = ldg_pinned(bn + boff[j]);    // refill the registers just consumed with the next k-step's fragment
+            if (FULL || j < nbv) bq[j] = ldg_pinned(bn + boff[j]);  // refill the registers just consumed (next k-step)
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) a_cur[i] = a_nxt[i];
@@ -516,13 +364,6 @@ int launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
 
 }  // namespace
 
-static int smem_sm_() {
-    int device = 0, v = 0;
-    cudaGetDevice(&device);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
-    return v;
-}
-
 bool dense_kernel_fits(int n_tab, int smem_optin) { return dense_smem_bytes(n_tab, 16) <= (size_t)smem_optin; }
 
 // CTA shape.  Many outputs: 16 warps x 4 output blocks (32 points x 512 outputs per CTA; the widest register tile, fewest
@@ -543,11 +384,6 @@ int dense_kernel_launch(const DenseArgs& a, const double* x, double* y, cudaStre
         const int groups = (a.nblk + 7) / 8, per = (a.nblk + groups - 1) / groups;
         if (per <= 4) return launch_splitk<16, 4>(a, x, y, st);
         return launch_splitk<8, 8>(a, x, y, st);
-    }
-    static const int want_unit = std::getenv("SMX_DENSE_UNIT") ? std::atoi(std::getenv("SMX_DENSE_UNIT")) : 0;
-    if (want_unit && !want_nb && a.nblk < 48) {
-        const bool two = 2 * (dense_smem_bytes(a.n_tab, 8) + 1024) <= (size_t)smem_sm_();
-        return two ? launch_unit<8, 4, 2>(a, x, y, st) : launch_unit<8, 4, 1>(a, x, y, st);
     }
     const int nb = want_nb ? want_nb : (a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1);
     const int nw = want_nw ? want_nw : (nb == 4 ? 16 : 8);
