@@ -93,6 +93,7 @@ struct FastDevice {
     int32_t* dense_meta = nullptr;
     double* dense_eta0 = nullptr;
     double* dense_coef = nullptr;
+    bool eta0_zero = true;          // every cold block has zero first centres (pi_{j,1} = x_j): kernel variant without the subtraction
     bool has_cold = false;          // some leading entries live on cold columns (their derivatives are block-sparse row sums)
     bool has_dense_grad = false;    // derivative sets as dense columns: smx_gradient = sparse kernel (cold columns) + dense kernel
     double* dense_grad_coef = nullptr;

@@ -66,6 +66,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     for (int32_t c = 0; c < plan.n_chunks; ++c) {
         if (!(plan.chunk_flags[c] & (kChunkHot | kChunkContig))) sparse_ok = false;
         if (!(plan.chunk_flags[c] & kChunkHot)) dev.has_cold = true;
+        if (!(plan.chunk_flags[c] & (kChunkHot | kChunkEtaZero))) dev.eta0_zero = false;
     }
     int device = 0, smem_optin = 0;
     SMX_CUDA(cudaGetDevice(&device));
@@ -141,7 +142,10 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
                 const int32_t c = (k & 1) ? l[--hi] : l[lo++];
                 dir[pos * 4 + 0] = kstep_off[c];
                 dir[pos * 4 + 1] = plan.chunk_dir[(size_t)c * 4 + 1];
-                dir[pos * 4 + 2] = plan.chunk_dir[(size_t)c * 4 + 2];
+                {   // flags | nf << 8, plus (lean kernel) the record size in 128-byte units << 16 and the k-steps << 24
+                    const int32_t ks = (plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4;
+                    dir[pos * 4 + 2] = (plan.chunk_dir[(size_t)c * 4 + 2] & 0xffff) | ((5 + 4 * ks) << 16) | (ks << 24);
+                }
                 dir[pos * 4 + 3] = plan.chunk_dir[(size_t)c * 4 + 3];
                 std::copy_n(&plan.chunk_meta[(size_t)c * kMetaInts], kMetaInts, &meta[pos * kMetaInts]);
                 // table rows -> offsets in doubles (saves the kernel a multiply per table access)

@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "smx_fast_device.cuh"
 
@@ -334,6 +335,249 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     }
 }
 
+// ---- lean variant of the FLAT kernel: values only -------------------------------------------------------------------------
+// Same data, same shared-memory layout, same arithmetic and summation order as fast_eval_kernel<NW, 2, 0, false, 2, true>;
+// what changes is the instruction count of the item loop (the kernel is bound by issue/dependency latency, not by HBM or
+// the FP64 pipe):
+//   * hot and cold items run separate straight-line bodies, so the 16 leading basis values stay in the registers their
+//     LDS.128 delivered them to (the merged body paid 32 register moves per cold item to reconcile the two layouts);
+//   * ETA0 (every cold first centre is zero, i.e. the default Leja domain): pi = x, no subtraction at all;
+//   * the directory entry of the next item is loaded once (warp-uniform) and carried into the next iteration;
+//   * the fragments of the second k-step are only loaded when the item has one (PRE1: before the first DMMAs, else after).
+// One lane of the warp issues the copies of an item (lean kernel): the record size comes pre-computed in the directory.
+__device__ __forceinline__ void stage_lean(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, const int4 dir, int o, int p0) {
+    const unsigned units = ((unsigned)dir.z >> 16) & 0xffu;  // record = metadata + coefficients, in units of 128 bytes
+    const unsigned bytes = units << 7;
+    const bool cold = !(dir.z & kChunkHot);
+    mbar_expect_tx(&st.bar[buf], bytes + (cold ? kXTileBytes : 0));
+    bulk_copy(&st.item[buf], reinterpret_cast<const unsigned char*>(a.coef) + ((size_t)(unsigned)(dir.x + o * (int)units) << 7), bytes, &st.bar[buf]);
+    if (cold) tma_load_2d(xs, xmap, dir.w, p0, &st.bar[buf]);
+}
+
+template <int NW, bool ETA0, bool PRE1>
+__global__ void __launch_bounds__(NW * 32, 2)
+fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
+    constexpr int kThreads = NW * 32;
+    // the dynamic shared memory starts on a 1 KiB boundary of the shared window (no static shared memory in this kernel; checked
+    // once below), so every buffer sits at a compile-time offset and no address has to be re-derived inside the item loop
+    extern __shared__ __align__(1024) unsigned char smem_lean[];
+    unsigned char* base = smem_lean;
+    if ((smem_u32(smem_lean) & 1023u) != 0) __trap();
+    XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
+    ItemStage* stages = reinterpret_cast<ItemStage*>(xtiles + NW);                // [NW]
+    double* tab = reinterpret_cast<double*>(stages + NW);                         // [1 + n_hot_rows][kTabPitch]
+    int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)(1 + a.n_hot_rows) * kTabPitch);
+    double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);
+    int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // (unused here: same carve-up as smem_bytes)
+    int* s_hot_off = reinterpret_cast<int*>(s_pairs + a.n_pairs);
+    int* s_hot_row = s_hot_off + a.hot_dims + 1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tig = lane & 3, gid = lane >> 2;
+    ItemStage& st = stages[warp];
+    double* xs = xtiles[warp].v;
+    const double* xlo = xs + gid * kBlockWidth + (((2 * tig) ^ gid) << 1);
+    const double* xhi = xs + gid * kBlockWidth + (((2 * tig + 1) ^ gid) << 1);
+    const double* tabq = tab + 2 * gid;
+
+    for (int i = tid; i < a.n_chunks; i += kThreads) s_dir[i] = __ldg(a.chunk_dir + i);
+    for (int i = tid; i < a.n_hot; i += kThreads) s_eta[i] = __ldg(a.eta + i);
+    for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
+    for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
+    if (lane == 0) {
+        mbar_init(&st.bar[0], 1);
+        mbar_init(&st.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double xhot[kHotRegs];
+    auto load_hot = [&](long long tile_p0) {
+        const double* xrow = x + min(tile_p0 + lane, a.N - 1) * a.ldx;
+#pragma unroll
+        for (int u = 0; u < kHotRegs; ++u) xhot[u] = (warp + NW * u < a.hot_dims) ? __ldg(xrow + warp + NW * u) : 0.0;
+    };
+    if ((long long)blockIdx.x < a.num_tiles) load_hot((long long)blockIdx.x * kTile);
+    __syncthreads();
+
+    unsigned k_item = 0;
+    const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
+
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int p0 = (int)(tile * kTile);  // (TMA coordinates are 32-bit: N < 2^31, checked at launch)
+        if (tid < kTile) tab[tid] = 1.0;
+        {
+            const int slot = t_slot(lane);
+            auto hot_dim = [&](int d, double xv) {
+                double v = 1.0;
+                for (int k = s_hot_off[d]; k < s_hot_off[d + 1]; ++k) {
+                    v *= (xv - s_eta[k]);
+                    tab[s_hot_row[k] * kTabPitch + slot] = v;
+                }
+            };
+#pragma unroll
+            for (int u = 0; u < kHotRegs; ++u)
+                if (warp + NW * u < a.hot_dims) hot_dim(warp + NW * u, xhot[u]);
+            if (a.hot_dims > NW * kHotRegs) {
+                const double* xrow = x + min((long long)p0 + lane, a.N - 1) * a.ldx;
+                for (int d = warp + NW * kHotRegs; d < a.hot_dims; d += NW) hot_dim(d, __ldg(xrow + d));
+            }
+        }
+        __syncthreads();
+        if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);
+
+        const int n_out = (int)a.d_out;
+        for (int o = 0; o < n_out; ++o) {
+            double tot[4] = {0.0, 0.0, 0.0, 0.0};
+            int4 dir = make_int4(0, 0, 0, 0);
+            if (c_begin < c_end) {
+                dir = s_dir[c_begin];
+                if (lane == 0) stage_lean(a, &xmap, st, xs, k_item & 1, dir, o, p0);
+            }
+            for (int c = c_begin; c < c_end; ++c, ++k_item) {
+                const int buf = k_item & 1;
+                const ItemBuffer& ib = st.item[buf];
+                const bool more = c + 1 < c_end;
+                const int4 ndir = s_dir[more ? c + 1 : c];
+                const int ksteps = (unsigned)dir.z >> 24;
+                const int nf = (dir.z >> 8) & 7;
+                mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
+
+                auto load_a = [&](int s, double2& lo, double2& hi) {  // A fragment of k-step s: 4 points of this lane's row
+                    const int4 f = ib.fac[4 * s + tig];
+                    lo = *reinterpret_cast<const double2*>(tabq + f.x);
+                    hi = *reinterpret_cast<const double2*>(tabq + f.x + 16);
+                    if (nf > 1) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(tabq + f.y);
+                        const double2 h2 = *reinterpret_cast<const double2*>(tabq + f.y + 16);
+                        lo.x *= l2.x, lo.y *= l2.y, hi.x *= h2.x, hi.y *= h2.y;
+                    }
+                    if (nf > 2) {
+                        const double2 l3 = *reinterpret_cast<const double2*>(tabq + f.z);
+                        const double2 h3 = *reinterpret_cast<const double2*>(tabq + f.z + 16);
+                        const double2 l4 = *reinterpret_cast<const double2*>(tabq + f.w);
+                        const double2 h4 = *reinterpret_cast<const double2*>(tabq + f.w + 16);
+                        lo.x *= l3.x * l4.x, lo.y *= l3.y * l4.y, hi.x *= h3.x * h4.x, hi.y *= h3.y * h4.y;
+                    }
+                };
+                // the whole item, instantiated once for hot and once for cold blocks
+                auto item = [&](auto hot_tag) {
+                    constexpr bool HOT = decltype(hot_tag)::value;
+                    double2 a0lo, a0hi, a1lo = make_double2(0.0, 0.0), a1hi = a1lo, b1 = a1lo;
+                    const double2 b0 = *reinterpret_cast<const double2*>(ib.coef + 2 * lane);
+                    load_a(0, a0lo, a0hi);
+                    if (PRE1 && ksteps > 1) {
+                        b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                        load_a(1, a1lo, a1hi);
+                    }
+                    // leading basis values of the lane's 4 points x 4 entries, as the eight LDS.128 deliver them:
+                    //   cold: q0[i] = entries (4 tig, 4 tig + 1), q1[i] = entries (4 tig + 2, 4 tig + 3) of point gid + 8 i
+                    //   hot : q0[e] = points (gid, gid + 8),      q1[e] = points (gid + 16, gid + 24)    of entry 4 tig + e
+                    // (hot: the values are rows of the value table, which outlives the item - they are read after the DMMAs,
+                    // when the A fragments are dead; only their four row offsets are taken from the item buffer now)
+                    double2 q0[4], q1[4];
+                    int4 t4 = make_int4(0, 0, 0, 0);
+                    if (HOT) {
+                        t4 = *reinterpret_cast<const int4*>(ib.tab + 4 * tig);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            q0[i] = *reinterpret_cast<const double2*>(xlo + i * (8 * kBlockWidth));
+                            q1[i] = *reinterpret_cast<const double2*>(xhi + i * (8 * kBlockWidth));
+                        }
+                        if (!ETA0 && !(dir.z & kChunkEtaZero)) {
+                            const double2 ea = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig);
+                            const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) q0[i].x -= ea.x, q0[i].y -= ea.y, q1[i].x -= eb.x, q1[i].y -= eb.y;
+                        }
+                    }
+                    __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
+                    if (more && lane == 0) stage_lean(a, &xmap, st, xs, buf ^ 1, ndir, o, p0);
+
+                    double acc[4][2][2];
+                    {
+                        const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            dmma_first<0>(acc[i][0], af[i], b0.x);
+                            dmma_first<0>(acc[i][1], af[i], b0.y);
+                        }
+                    }
+                    if (ksteps > 1) {
+                        if (!PRE1) {
+                            b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                            load_a(1, a1lo, a1hi);
+                        }
+                        const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            dmma_<0>(acc[i][0], af[i], b1.x);
+                            dmma_<0>(acc[i][1], af[i], b1.y);
+                        }
+#pragma unroll 1
+                        for (int s = 2; s < ksteps; ++s) {
+                            double2 a01, a23;
+                            load_a(s, a01, a23);
+                            const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
+                            const double ag[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                dmma_<0>(acc[i][0], ag[i], b.x);
+                                dmma_<0>(acc[i][1], ag[i], b.y);
+                            }
+                        }
+                    }
+                    if (HOT) {
+                        const int tabs[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            q0[e] = *reinterpret_cast<const double2*>(tabq + tabs[e]);
+                            q1[e] = *reinterpret_cast<const double2*>(tabq + tabs[e] + 16);
+                        }
+                        const double v[4][4] = {{q0[0].x, q0[1].x, q0[2].x, q0[3].x}, {q0[0].y, q0[1].y, q0[2].y, q0[3].y},
+                                                {q1[0].x, q1[1].x, q1[2].x, q1[3].x}, {q1[0].y, q1[1].y, q1[2].y, q1[3].y}};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            tot[i] = fma(v[i][0], acc[i][0][0], tot[i]);
+                            tot[i] = fma(v[i][1], acc[i][0][1], tot[i]);
+                            tot[i] = fma(v[i][2], acc[i][1][0], tot[i]);
+                            tot[i] = fma(v[i][3], acc[i][1][1], tot[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            tot[i] = fma(q0[i].x, acc[i][0][0], tot[i]);
+                            tot[i] = fma(q0[i].y, acc[i][0][1], tot[i]);
+                            tot[i] = fma(q1[i].x, acc[i][1][0], tot[i]);
+                            tot[i] = fma(q1[i].y, acc[i][1][1], tot[i]);
+                        }
+                    }
+                };
+                if (dir.z & kChunkHot) item(std::true_type{});
+                else item(std::false_type{});
+                dir = ndir;
+            }
+            // ---- epilogue: as in fast_eval_kernel ----------------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tot[i] += __shfl_xor_sync(0xffffffffu, tot[i], 1);
+                tot[i] += __shfl_xor_sync(0xffffffffu, tot[i], 2);
+            }
+            if (tig == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xs[gid + 8 * i] = tot[i];
+            }
+            __syncthreads();
+            if (tid < kTile && (long long)p0 + tid < a.N) {
+                double s = __ldg(a.c0 + o);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
+                y[((long long)p0 + tid) * a.d_out + o] = s;
+            }
+            if (o + 1 < n_out) __syncthreads();
+        }
+    }
+}
+
 size_t smem_bytes(const FastDevice& d, int nw, bool flat = false) {
     const size_t rows = flat ? 1 + (size_t)d.n_hot_rows : (size_t)d.n_tab;
     return 1024 + (size_t)nw * (sizeof(XTile) + sizeof(ItemStage)) + (rows * kTabPitch + (size_t)d.n_hot) * sizeof(double) + (flat ? 0 : (size_t)d.n_flat * sizeof(int4)) + 16 +
@@ -369,6 +613,21 @@ int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const
     return SMX_OK;
 }
 
+template <int NW, bool ETA0, bool PRE1>
+int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
+    const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * 2);
+    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, true)));
+    fast_lean_kernel<NW, ETA0, PRE1><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, true), st>>>(map, a, x, y);
+    SMX_LAUNCH_CHECK("fast_lean_kernel");
+    return SMX_OK;
+}
+template <int NW>
+int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
+    static const int pre1 = std::getenv("SMX_FAST_PRE1") ? std::atoi(std::getenv("SMX_FAST_PRE1")) : 0;  // tuning knob (measured: 1.955 vs 2.007 ms)
+    if (d.eta0_zero) return pre1 ? launch_lean2<NW, true, true>(map, a, d, x, y, st) : launch_lean2<NW, true, false>(map, a, d, x, y, st);
+    return pre1 ? launch_lean2<NW, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false>(map, a, d, x, y, st);
+}
+
 }  // namespace
 
 // Chooses the CTA shape for this plan and opts into the shared memory it needs.
@@ -398,9 +657,9 @@ int fast_kernel_prepare(FastDevice& d) {
             return SMX_OK;
         }
     }
-    if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 6)) {
-        for (int nw : {8, 6}) {
-            if (want != 0 && want != nw) continue;
+    if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 7 || want == 6)) {
+        for (int nw : {8, 7, 6}) {
+            if (want != nw && (want != 0 || nw == 7)) continue;  // (7 only on request)
             if (2 * (smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) {
                 d.flat = true;
                 d.warps = nw;
@@ -444,8 +703,17 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
     if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
     if (d.flat) {
+        if (a.gradient && d.warps == 7) return fail(SMX_ERR_UNSUPPORTED, "7 warps per CTA: lean kernel only (tuning knob)");
         if (a.gradient && d.warps == 12) return launch<12, 1, 0, true, 2, true>(map, a, d, x, y, st);
         if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
+        // values: the lean item loop (SMX_FAST_LEAN=0 selects the general kernel, for A/B timing)
+        static const int lean = std::getenv("SMX_FAST_LEAN") ? std::atoi(std::getenv("SMX_FAST_LEAN")) : 1;
+        if (lean && a.N < (1ll << 31) - kTile) {
+            if (d.warps == 8) return launch_lean<8>(map, a, d, x, y, st);
+            if (d.warps == 7) return launch_lean<7>(map, a, d, x, y, st);
+            if (d.warps == 6) return launch_lean<6>(map, a, d, x, y, st);
+        }
+        if (d.warps == 7) return fail(SMX_ERR_UNSUPPORTED, "7 warps per CTA: lean kernel only (tuning knob)");
         return d.warps == 8 ? launch<8, 2, 0, false, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, false, 2, true>(map, a, d, x, y, st);
     }
     if (a.gradient) {
