@@ -345,12 +345,15 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 //   * the directory entry of the next item is loaded once (warp-uniform) and carried into the next iteration;
 //   * the fragments of the second k-step are only loaded when the item has one (PRE1: before the first DMMAs, else after).
 // One lane of the warp issues the copies of an item (lean kernel): the record size comes pre-computed in the directory.
-__device__ __forceinline__ void stage_lean(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, const int4 dir, int o, int p0) {
-    const unsigned units = ((unsigned)dir.z >> 16) & 0xffu;  // record = metadata + coefficients, in units of 128 bytes
-    const unsigned bytes = units << 7;
+// The shared-memory directory of the lean kernel holds, per item: the global address of its first record (x, y), then
+// flags | nf << 8 | record size in 128-byte units << 16 | k-steps << 24 (z; bit 7 = last item of its warp), first column (w).
+constexpr int kDirLast = 0x80;
+__device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, const int4 dir, int o, int p0) {
+    const unsigned bytes = ((unsigned)dir.z >> 9) & 0x7f80u;  // record = metadata + coefficients
     const bool cold = !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], bytes + (cold ? kXTileBytes : 0));
-    bulk_copy(&st.item[buf], reinterpret_cast<const unsigned char*>(a.coef) + ((size_t)(unsigned)(dir.x + o * (int)units) << 7), bytes, &st.bar[buf]);
+    const unsigned long long src = ((unsigned long long)(unsigned)dir.y << 32 | (unsigned)dir.x) + (unsigned long long)((unsigned)o * bytes);
+    bulk_copy(&st.item[buf], reinterpret_cast<const void*>(src), bytes, &st.bar[buf]);
     if (cold) tma_load_2d(xs, xmap, dir.w, p0, &st.bar[buf]);
 }
 
@@ -380,7 +383,11 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     const double* xhi = xs + gid * kBlockWidth + (((2 * tig + 1) ^ gid) << 1);
     const double* tabq = tab + 2 * gid;
 
-    for (int i = tid; i < a.n_chunks; i += kThreads) s_dir[i] = __ldg(a.chunk_dir + i);
+    for (int i = tid; i < a.n_chunks; i += kThreads) {
+        const int4 d = __ldg(a.chunk_dir + i);
+        const unsigned long long src = reinterpret_cast<unsigned long long>(a.coef) + ((unsigned long long)(unsigned)d.x << 7);
+        s_dir[i] = make_int4((int)(unsigned)src, (int)(unsigned)(src >> 32), d.z, d.w);
+    }
     for (int i = tid; i < a.n_hot; i += kThreads) s_eta[i] = __ldg(a.eta + i);
     for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
     for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
@@ -397,9 +404,12 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     };
     if ((long long)blockIdx.x < a.num_tiles) load_hot((long long)blockIdx.x * kTile);
     __syncthreads();
+    if (tid < NW && a.warp_off[tid] < a.warp_off[tid + 1]) s_dir[a.warp_off[tid + 1] - 1].z |= kDirLast;
+    __syncthreads();
 
     unsigned k_item = 0;
-    const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
+    const int4* const dir_begin = s_dir + a.warp_off[warp];
+    const bool has_items = a.warp_off[warp] < a.warp_off[warp + 1];
 
     for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int p0 = (int)(tile * kTile);  // (TMA coordinates are 32-bit: N < 2^31, checked at launch)
@@ -428,15 +438,17 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         for (int o = 0; o < n_out; ++o) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             int4 dir = make_int4(0, 0, 0, 0);
-            if (c_begin < c_end) {
-                dir = s_dir[c_begin];
-                if (lane == 0) stage_lean(a, &xmap, st, xs, k_item & 1, dir, o, p0);
+            const int4* dp = dir_begin;
+            bool more = has_items;
+            if (has_items) {
+                dir = *dp;
+                if (lane == 0) stage_lean(&xmap, st, xs, k_item & 1, dir, o, p0);
             }
-            for (int c = c_begin; c < c_end; ++c, ++k_item) {
+            for (; more; ++k_item) {
                 const int buf = k_item & 1;
                 const ItemBuffer& ib = st.item[buf];
-                const bool more = c + 1 < c_end;
-                const int4 ndir = s_dir[more ? c + 1 : c];
+                more = !(dir.z & kDirLast);
+                const int4 ndir = *++dp;  // (one slot past the warp's list at its last item: still inside the carve-up, unused)
                 const int ksteps = (unsigned)dir.z >> 24;
                 const int nf = (dir.z >> 8) & 7;
                 mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
@@ -491,7 +503,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         }
                     }
                     __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                    if (more && lane == 0) stage_lean(a, &xmap, st, xs, buf ^ 1, ndir, o, p0);
+                    if (more && lane == 0) stage_lean(&xmap, st, xs, buf ^ 1, ndir, o, p0);
 
                     double acc[4][2][2];
                     {
