@@ -348,16 +348,28 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 // The shared-memory directory of the lean kernel holds, per item: the global address of its first record (x, y), then
 // flags | nf << 8 | record size in 128-byte units << 16 | k-steps << 24 (z; bit 7 = last item of its warp), first column (w).
 constexpr int kDirLast = 0x80;
-__device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, const int4 dir, int o, int p0) {
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Item buffer + its mbarrier; the two of a warp sit back to back, so ONE signed stride flips every pointer into them.
+struct alignas(16) LeanStage {
+    ItemBuffer item;
+    unsigned long long bar, pad;
+};
+static_assert(2 * sizeof(LeanStage) <= sizeof(ItemStage) + 32, "the lean layout uses the alignment slack of the carve-up");
+__device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* item, const void* bar, double* xs, const int4 dir, int o, int p0) {
     const unsigned bytes = ((unsigned)dir.z >> 9) & 0x7f80u;  // record = metadata + coefficients
     const bool cold = !(dir.z & kChunkHot);
-    mbar_expect_tx(&st.bar[buf], bytes + (cold ? kXTileBytes : 0));
+    unsigned long long* b = const_cast<unsigned long long*>(static_cast<const unsigned long long*>(bar));
+    mbar_expect_tx(b, bytes + (cold ? kXTileBytes : 0));
     const unsigned long long src = ((unsigned long long)(unsigned)dir.y << 32 | (unsigned)dir.x) + (unsigned long long)((unsigned)o * bytes);
-    bulk_copy(&st.item[buf], reinterpret_cast<const void*>(src), bytes, &st.bar[buf]);
-    if (cold) tma_load_2d(xs, xmap, dir.w, p0, &st.bar[buf]);
+    bulk_copy(const_cast<void*>(item), reinterpret_cast<const void*>(src), bytes, b);
+    if (cold) tma_load_2d(xs, xmap, dir.w, p0, b);
 }
 
-template <int NW, bool ETA0, bool PRE1>
+template <int NW, bool ETA0, bool PRE1, bool ELECT>
 __global__ void __launch_bounds__(NW * 32, 2)
 fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -367,8 +379,8 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     unsigned char* base = smem_lean;
     if ((smem_u32(smem_lean) & 1023u) != 0) __trap();
     XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
-    ItemStage* stages = reinterpret_cast<ItemStage*>(xtiles + NW);                // [NW]
-    double* tab = reinterpret_cast<double*>(stages + NW);                         // [1 + n_hot_rows][kTabPitch]
+    LeanStage* stages = reinterpret_cast<LeanStage*>(xtiles + NW);                // [NW][2]
+    double* tab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(stages) + NW * (sizeof(ItemStage) + 32));  // [1 + n_hot_rows][kTabPitch]
     int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)(1 + a.n_hot_rows) * kTabPitch);
     double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);
     int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // (unused here: same carve-up as smem_bytes)
@@ -377,11 +389,20 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tig = lane & 3, gid = lane >> 2;
-    ItemStage& st = stages[warp];
+    LeanStage* st = stages + 2 * warp;
     double* xs = xtiles[warp].v;
+    // Lane pointers.  All of them are carried through the item loop by an addition (the three into the item buffers flip
+    // between the two buffers, the others add a run-time zero), so that they LIVE in registers: left as loop invariants
+    // they were re-derived from the thread index in every iteration (~25 instructions per item at the 128-register cap).
     const double* xlo = xs + gid * kBlockWidth + (((2 * tig) ^ gid) << 1);
     const double* xhi = xs + gid * kBlockWidth + (((2 * tig + 1) ^ gid) << 1);
     const double* tabq = tab + 2 * gid;
+    const unsigned char* ibt = reinterpret_cast<const unsigned char*>(&st[0].item) + 16 * tig;    // + offsetof(tab | fac)
+    const unsigned char* ibl = reinterpret_cast<const unsigned char*>(&st[0].item) + offsetof(ItemBuffer, coef) + 16 * lane;
+    const unsigned char* barp = reinterpret_cast<const unsigned char*>(&st[0].bar);
+    int flip = (int)sizeof(LeanStage);
+    const int zero = a.gradient;  // 0 in this kernel; the compiler cannot know
+    const double* xsp = xs;       // (warp-uniform: destination of the x tile for the electing variant)
 
     for (int i = tid; i < a.n_chunks; i += kThreads) {
         const int4 d = __ldg(a.chunk_dir + i);
@@ -392,8 +413,8 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     for (int i = tid; i <= a.hot_dims; i += kThreads) s_hot_off[i] = __ldg(a.hot_off + i);
     for (int i = tid; i < a.n_hot; i += kThreads) s_hot_row[i] = 1 + hot_row(__ldg(a.hot_pos + i));
     if (lane == 0) {
-        mbar_init(&st.bar[0], 1);
-        mbar_init(&st.bar[1], 1);
+        mbar_init(&st[0].bar, 1);
+        mbar_init(&st[1].bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     double xhot[kHotRegs];
@@ -442,19 +463,21 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             bool more = has_items;
             if (has_items) {
                 dir = *dp;
-                if (lane == 0) stage_lean(&xmap, st, xs, k_item & 1, dir, o, p0);
+                if (ELECT) {
+                    if (elect_one()) stage_lean(&xmap, barp - sizeof(ItemBuffer), barp, const_cast<double*>(xsp), dir, o, p0);
+                } else {
+                    if (lane == 0) stage_lean(&xmap, ibt, barp, const_cast<double*>(xlo), dir, o, p0);  // (lane 0: ibt = the buffer, xlo = the x tile)
+                }
             }
             for (; more; ++k_item) {
-                const int buf = k_item & 1;
-                const ItemBuffer& ib = st.item[buf];
                 more = !(dir.z & kDirLast);
                 const int4 ndir = *++dp;  // (one slot past the warp's list at its last item: still inside the carve-up, unused)
                 const int ksteps = (unsigned)dir.z >> 24;
                 const int nf = (dir.z >> 8) & 7;
-                mbar_wait(&st.bar[buf], (k_item >> 1) & 1);
+                mbar_wait(const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(barp)), (k_item >> 1) & 1);
 
                 auto load_a = [&](int s, double2& lo, double2& hi) {  // A fragment of k-step s: 4 points of this lane's row
-                    const int4 f = ib.fac[4 * s + tig];
+                    const int4 f = *reinterpret_cast<const int4*>(ibt + offsetof(ItemBuffer, fac) + 64 * s);
                     lo = *reinterpret_cast<const double2*>(tabq + f.x);
                     hi = *reinterpret_cast<const double2*>(tabq + f.x + 16);
                     if (nf > 1) {
@@ -474,10 +497,10 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 auto item = [&](auto hot_tag) {
                     constexpr bool HOT = decltype(hot_tag)::value;
                     double2 a0lo, a0hi, a1lo = make_double2(0.0, 0.0), a1hi = a1lo, b1 = a1lo;
-                    const double2 b0 = *reinterpret_cast<const double2*>(ib.coef + 2 * lane);
+                    const double2 b0 = *reinterpret_cast<const double2*>(ibl);
                     load_a(0, a0lo, a0hi);
                     if (PRE1 && ksteps > 1) {
-                        b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                        b1 = *reinterpret_cast<const double2*>(ibl + 8 * kKStepDoubles);
                         load_a(1, a1lo, a1hi);
                     }
                     // leading basis values of the lane's 4 points x 4 entries, as the eight LDS.128 deliver them:
@@ -488,7 +511,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     double2 q0[4], q1[4];
                     int4 t4 = make_int4(0, 0, 0, 0);
                     if (HOT) {
-                        t4 = *reinterpret_cast<const int4*>(ib.tab + 4 * tig);
+                        t4 = *reinterpret_cast<const int4*>(ibt);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -496,14 +519,18 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                             q1[i] = *reinterpret_cast<const double2*>(xhi + i * (8 * kBlockWidth));
                         }
                         if (!ETA0 && !(dir.z & kChunkEtaZero)) {
-                            const double2 ea = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig);
-                            const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
+                            const double2 ea = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig);
+                            const double2 eb = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig + 16);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) q0[i].x -= ea.x, q0[i].y -= ea.y, q1[i].x -= eb.x, q1[i].y -= eb.y;
                         }
                     }
                     __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                    if (more && lane == 0) stage_lean(&xmap, st, xs, buf ^ 1, ndir, o, p0);
+                    if (ELECT) {  // one elected lane, warp-uniform operands: no per-lane-value loops around the copy instructions
+                        if (more && elect_one()) stage_lean(&xmap, barp + flip - sizeof(ItemBuffer), barp + flip, const_cast<double*>(xsp), ndir, o, p0);
+                    } else {
+                        if (more && lane == 0) stage_lean(&xmap, ibt + flip, barp + flip, const_cast<double*>(xlo), ndir, o, p0);
+                    }
 
                     double acc[4][2][2];
                     {
@@ -516,7 +543,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                     if (ksteps > 1) {
                         if (!PRE1) {
-                            b1 = *reinterpret_cast<const double2*>(ib.coef + kKStepDoubles + 2 * lane);
+                            b1 = *reinterpret_cast<const double2*>(ibl + 8 * kKStepDoubles);
                             load_a(1, a1lo, a1hi);
                         }
                         const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
@@ -529,7 +556,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         for (int s = 2; s < ksteps; ++s) {
                             double2 a01, a23;
                             load_a(s, a01, a23);
-                            const double2 b = *reinterpret_cast<const double2*>(ib.coef + s * kKStepDoubles + 2 * lane);
+                            const double2 b = *reinterpret_cast<const double2*>(ibl + 8 * kKStepDoubles * s);
                             const double ag[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -567,6 +594,9 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 if (dir.z & kChunkHot) item(std::true_type{});
                 else item(std::false_type{});
                 dir = ndir;
+                ibt += flip, ibl += flip, barp += flip, flip = -flip;
+                xlo += zero, xhi += zero, tabq += zero;
+                if (ELECT) xsp += zero;
             }
             // ---- epilogue: as in fast_eval_kernel ----------------------------------------------------------------------
 #pragma unroll
@@ -625,19 +655,19 @@ int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const
     return SMX_OK;
 }
 
-template <int NW, bool ETA0, bool PRE1>
+template <int NW, bool ETA0, bool PRE1, bool ELECT>
 int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * 2);
-    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, true)));
-    fast_lean_kernel<NW, ETA0, PRE1><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, true), st>>>(map, a, x, y);
+    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, true)));
+    fast_lean_kernel<NW, ETA0, PRE1, ELECT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, true), st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_lean_kernel");
     return SMX_OK;
 }
 template <int NW>
 int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
-    static const int pre1 = std::getenv("SMX_FAST_PRE1") ? std::atoi(std::getenv("SMX_FAST_PRE1")) : 0;  // tuning knob (measured: 1.955 vs 2.007 ms)
-    if (d.eta0_zero) return pre1 ? launch_lean2<NW, true, true>(map, a, d, x, y, st) : launch_lean2<NW, true, false>(map, a, d, x, y, st);
-    return pre1 ? launch_lean2<NW, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false>(map, a, d, x, y, st);
+    static const int elect = std::getenv("SMX_FAST_ELECT") ? std::atoi(std::getenv("SMX_FAST_ELECT")) : 1;  // tuning knob (measured: 1.847 vs 1.888 ms)
+    if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true>(map, a, d, x, y, st);
+    return d.eta0_zero ? launch_lean2<NW, true, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false>(map, a, d, x, y, st);
 }
 
 }  // namespace
