@@ -291,10 +291,11 @@ def main():
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-            "kernel": "fast_eval_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel": "fast_multi_kernel" if 2 <= d_loc <= 6 else "fast_lean_kernel", "algorithmic_bytes_per_launch": alg_bytes,
             "fp64_tflops_executed": fp64_tflops, "fp64_dmma_peak_tflops_measured": fp64_peak,
             "note": "x is streamed once (8*(d_in+d_out) B per point); the FP64 tensor work (2*padded_fma flop per point) "
-                    "needs 0.94 ms per 1e6 points at the measured DMMA peak, the x stream 1.24 ms at the measured HBM peak",
+                    f"needs {2.0 * fma_per_eval * d_loc * n_points / ((fp64_peak or 37.12) * 1e12) * 1e3:.2f} ms per launch at the measured DMMA peak, "
+                    f"the x stream {alg_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3:.2f} ms at the measured HBM peak",
         }
         if dense:
             # GEMM regime (folded form): algorithmic flops = 2 * d_out * n_terms per point, on the FP64 tensor
