@@ -104,6 +104,8 @@ struct FastDevice {
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
     bool flat_ok = false;  // every row has a factor list: the kernel variant without product rows can run
     bool flat = false;     // .. and is the one chosen (8 warps, two CTAs per SM)
+    bool deep_ok = false;  // hot parts of five to eight pairs: the plan carries a second factor list per row slot ..
+    bool deep = false;     // .. and the eight-factor lean kernel is the one chosen (values only)
     int multi = 0;         // > 0: values run the multi-set kernel with that many coefficient sets per pass (2 <= d_out < 32)
 };
 int fast_upload(const FastPlan& plan, FastDevice& dev);

@@ -98,9 +98,9 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
             if ((rc = upload(plan.dense_grad_col, &dev.dense_grad_col, dev.bytes))) return rc;
             dev.has_dense_grad = true;
         }
-    } else if (plan.has_dense_grad) {
-        return fail(SMX_ERR_UNSUPPORTED, "value table does not fit in shared memory");  // (the sparse sets were not built)
     }
+    // (else: the product table is too large for the GEMM-regime kernel.  Values run the block-sparse kernel, one output per
+    // pass; if the derivative sets were only built as dense columns, grad_ok stays false and the gradient runs per summand.)
     if (!sparse_ok) {
         if (!dev.has_dense)
             return fail(SMX_ERR_UNSUPPORTED, plan.has_sparse ? "plan has a cold block that is not a contiguous tile of x"
@@ -108,6 +108,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         return SMX_OK;
     }
     dev.flat_ok = plan.flat_ok;
+    dev.deep_ok = !plan.flat_ok && plan.deep_ok;  // hot parts of five to eight pairs: records with a second factor list
     if ((rc = fast_kernel_prepare(dev))) return dev.has_dense ? SMX_OK : rc;
 
     std::vector<double> packed;
@@ -117,6 +118,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     // warps (cost ~ fixed part + k-steps), then every warp alternates big and small items so that tensor-heavy and
     // streaming items are always in flight together.  Directory and metadata records are stored in that order.
     std::vector<int32_t> dir((size_t)plan.n_chunks * 4), meta((size_t)plan.n_chunks * kMetaInts);
+    std::vector<int32_t> fac2(dev.deep ? (size_t)plan.n_chunks * 64 : 0);  // deep records: factors 5..8 of every row slot
     {
         const int nw = dev.warps;
         double ca = 2.0, cb = 1.0, cc = 0.0;  // cost model of an item: fixed + per k-step + extra for streaming x
@@ -144,8 +146,10 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
                 dir[pos * 4 + 1] = plan.chunk_dir[(size_t)c * 4 + 1];
                 {   // flags | nf << 8, plus (lean kernel) the record size in 128-byte units << 16 and the k-steps << 24
                     const int32_t ks = (plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4;
-                    dir[pos * 4 + 2] = (plan.chunk_dir[(size_t)c * 4 + 2] & 0xffff) | ((5 + 4 * ks) << 16) | (ks << 24);
+                    dir[pos * 4 + 2] = (plan.chunk_dir[(size_t)c * 4 + 2] & 0xffff) | ((5 + 4 * ks + (dev.deep ? 2 : 0)) << 16) | (ks << 24);
                 }
+                if (dev.deep)
+                    for (int i = 0; i < 64; ++i) fac2[pos * 64 + i] = plan.chunk_fac2[(size_t)c * 64 + i] * kTabPitch;
                 dir[pos * 4 + 3] = plan.chunk_dir[(size_t)c * 4 + 3];
                 std::copy_n(&plan.chunk_meta[(size_t)c * kMetaInts], kMetaInts, &meta[pos * kMetaInts]);
                 // table rows -> offsets in doubles (saves the kernel a multiply per table access)
@@ -164,7 +168,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         std::vector<double> records;
         const size_t nsets = (size_t)plan.n_sets;
         size_t units = 0;
-        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) units += nsets * (5 + 4 * (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4));
+        const size_t extra = dev.deep ? 2 : 0;  // deep records end with the second factor list (256 bytes)
+        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) units += nsets * (5 + extra + 4 * (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4));
         if (units >= (size_t)INT32_MAX) return fail(SMX_ERR_UNSUPPORTED, "too many coefficient sets for the block-sparse form");
         records.assign(units * 16, 0.0);
         size_t at = 0;
@@ -174,7 +179,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
             for (size_t o = 0; o < nsets; ++o) {
                 std::memcpy(&records[at * 16], &meta[(size_t)pos * kMetaInts], kMetaInts * 4);
                 std::memcpy(&records[(at + 5) * 16], &packed[(k0 + o * ksteps) * kKStepDoubles], ksteps * kKStepDoubles * 8);
-                at += 5 + 4 * ksteps;
+                if (dev.deep) std::memcpy(&records[(at + 5 + 4 * ksteps) * 16], &fac2[(size_t)pos * 64], 256);
+                at += 5 + extra + 4 * ksteps;
             }
         }
         std::vector<double>().swap(packed);
@@ -183,8 +189,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
     dev.n_sets = plan.n_sets;
     dev.n_gd = (int32_t)plan.grad_dims.size();
-    dev.grad_ok = dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
-                                         (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0));
+    dev.grad_ok = !dev.deep && (dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
+                                         (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0)));
     if ((rc = upload(plan.grad_dims, &dev.grad_dims, dev.bytes))) return rc;
     dev.has_sparse = true;
     return SMX_OK;

@@ -354,11 +354,22 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 // Item buffer + its mbarrier; the two of a warp sit back to back, so ONE signed stride flips every pointer into them.
+// DEEP (hot parts of five to eight pairs): the record ends with a second factor list, factors 5..8 of every row slot,
+// which lands right behind the item's coefficients (at most at `fac2`).
+template <bool DEEP>
 struct alignas(16) LeanStage {
     ItemBuffer item;
     unsigned long long bar, pad;
 };
-static_assert(2 * sizeof(LeanStage) <= sizeof(ItemStage) + 32, "the lean layout uses the alignment slack of the carve-up");
+template <>
+struct alignas(16) LeanStage<true> {
+    ItemBuffer item;
+    int4 fac2[16];
+    unsigned long long bar, pad;
+};
+static_assert(2 * sizeof(LeanStage<false>) <= sizeof(ItemStage) + 32, "the lean layout uses the alignment slack of the carve-up");
+template <bool DEEP>
+__host__ __device__ constexpr size_t lean_stage_bytes() { return DEEP ? 2 * sizeof(LeanStage<true>) : sizeof(ItemStage) + 32; }  // per warp
 __device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* item, const void* bar, double* xs, const int4 dir, int o, int p0) {
     const unsigned bytes = ((unsigned)dir.z >> 9) & 0x7f80u;  // record = metadata + coefficients
     const bool cold = !(dir.z & kChunkHot);
@@ -369,7 +380,7 @@ __device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* 
     if (cold) tma_load_2d(xs, xmap, dir.w, p0, b);
 }
 
-template <int NW, bool ETA0, bool PRE1, bool ELECT>
+template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP = false>
 __global__ void __launch_bounds__(NW * 32, 2)
 fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -379,8 +390,9 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     unsigned char* base = smem_lean;
     if ((smem_u32(smem_lean) & 1023u) != 0) __trap();
     XTile* xtiles = reinterpret_cast<XTile*>(base);                               // [NW]
-    LeanStage* stages = reinterpret_cast<LeanStage*>(xtiles + NW);                // [NW][2]
-    double* tab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(stages) + NW * (sizeof(ItemStage) + 32));  // [1 + n_hot_rows][kTabPitch]
+    using Stage = LeanStage<DEEP>;
+    Stage* stages = reinterpret_cast<Stage*>(xtiles + NW);                        // [NW][2]
+    double* tab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(stages) + NW * lean_stage_bytes<DEEP>());  // [1 + n_hot_rows][kTabPitch]
     int4* s_dir = reinterpret_cast<int4*>(tab + (size_t)(1 + a.n_hot_rows) * kTabPitch);
     double* s_eta = reinterpret_cast<double*>(s_dir + a.n_chunks);
     int2* s_pairs = reinterpret_cast<int2*>(s_eta + a.n_hot);                     // (unused here: same carve-up as smem_bytes)
@@ -389,7 +401,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tig = lane & 3, gid = lane >> 2;
-    LeanStage* st = stages + 2 * warp;
+    Stage* st = stages + 2 * warp;
     double* xs = xtiles[warp].v;
     // Lane pointers.  All of them are carried through the item loop by an addition (the three into the item buffers flip
     // between the two buffers, the others add a run-time zero), so that they LIVE in registers: left as loop invariants
@@ -400,7 +412,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
     const unsigned char* ibt = reinterpret_cast<const unsigned char*>(&st[0].item) + 16 * tig;    // + offsetof(tab | fac)
     const unsigned char* ibl = reinterpret_cast<const unsigned char*>(&st[0].item) + offsetof(ItemBuffer, coef) + 16 * lane;
     const unsigned char* barp = reinterpret_cast<const unsigned char*>(&st[0].bar);
-    int flip = (int)sizeof(LeanStage);
+    int flip = (int)sizeof(Stage);
     const int zero = a.gradient;  // 0 in this kernel; the compiler cannot know
     const double* xsp = xs;       // (warp-uniform: destination of the x tile for the electing variant)
 
@@ -456,7 +468,8 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);
 
         const int n_out = (int)a.d_out;
-        for (int o = 0; o < n_out; ++o) {
+        // (outputs are spread over gridDim.y when there are fewer tiles than CTA slots: small batches, many outputs)
+        for (int o = blockIdx.y; o < n_out; o += gridDim.y) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             int4 dir = make_int4(0, 0, 0, 0);
             const int4* dp = dir_begin;
@@ -464,7 +477,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             if (has_items) {
                 dir = *dp;
                 if (ELECT) {
-                    if (elect_one()) stage_lean(&xmap, barp - sizeof(ItemBuffer), barp, const_cast<double*>(xsp), dir, o, p0);
+                    if (elect_one()) stage_lean(&xmap, barp - offsetof(Stage, bar), barp, const_cast<double*>(xsp), dir, o, p0);
                 } else {
                     if (lane == 0) stage_lean(&xmap, ibt, barp, const_cast<double*>(xlo), dir, o, p0);  // (lane 0: ibt = the buffer, xlo = the x tile)
                 }
@@ -473,7 +486,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 more = !(dir.z & kDirLast);
                 const int4 ndir = *++dp;  // (one slot past the warp's list at its last item: still inside the carve-up, unused)
                 const int ksteps = (unsigned)dir.z >> 24;
-                const int nf = (dir.z >> 8) & 7;
+                const int nf = (dir.z >> 8) & (DEEP ? 15 : 7);
                 mbar_wait(const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(barp)), (k_item >> 1) & 1);
 
                 auto load_a = [&](int s, double2& lo, double2& hi) {  // A fragment of k-step s: 4 points of this lane's row
@@ -491,6 +504,16 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         const double2 l4 = *reinterpret_cast<const double2*>(tabq + f.w);
                         const double2 h4 = *reinterpret_cast<const double2*>(tabq + f.w + 16);
                         lo.x *= l3.x * l4.x, lo.y *= l3.y * l4.y, hi.x *= h3.x * h4.x, hi.y *= h3.y * h4.y;
+                    }
+                    if (DEEP && nf > 4) {  // factors 5..8 (the ones row pads): second list, behind the item's coefficients
+                        const int4 g = *reinterpret_cast<const int4*>(ibt + offsetof(ItemBuffer, coef) + 8 * kKStepDoubles * ksteps + 64 * s);
+                        const int rows4[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double2 l5 = *reinterpret_cast<const double2*>(tabq + rows4[u]);
+                            const double2 h5 = *reinterpret_cast<const double2*>(tabq + rows4[u] + 16);
+                            lo.x *= l5.x, lo.y *= l5.y, hi.x *= h5.x, hi.y *= h5.y;
+                        }
                     }
                 };
                 // the whole item, instantiated once for hot and once for cold blocks
@@ -527,7 +550,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                     __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
                     if (ELECT) {  // one elected lane, warp-uniform operands: no per-lane-value loops around the copy instructions
-                        if (more && elect_one()) stage_lean(&xmap, barp + flip - sizeof(ItemBuffer), barp + flip, const_cast<double*>(xsp), ndir, o, p0);
+                        if (more && elect_one()) stage_lean(&xmap, barp + flip - offsetof(Stage, bar), barp + flip, const_cast<double*>(xsp), ndir, o, p0);
                     } else {
                         if (more && lane == 0) stage_lean(&xmap, ibt + flip, barp + flip, const_cast<double*>(xlo), ndir, o, p0);
                     }
@@ -615,7 +638,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
                 y[((long long)p0 + tid) * a.d_out + o] = s;
             }
-            if (o + 1 < n_out) __syncthreads();
+            if (o + (int)gridDim.y < n_out) __syncthreads();
         }
     }
 }
@@ -655,19 +678,27 @@ int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const
     return SMX_OK;
 }
 
-template <int NW, bool ETA0, bool PRE1, bool ELECT>
+size_t lean_smem_bytes(const FastDevice& d, int nw, bool deep) {
+    return smem_bytes(d, nw, true) + (deep ? (size_t)nw * (lean_stage_bytes<true>() - lean_stage_bytes<false>()) : 0);
+}
+
+template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP>
 int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
-    const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * 2);
-    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, true)));
-    fast_lean_kernel<NW, ETA0, PRE1, ELECT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, true), st>>>(map, a, x, y);
+    const long long slots = (long long)d.sm_count * 2, grid = std::min<long long>(a.num_tiles, slots);
+    // fewer tiles than CTA slots: split the outputs over gridDim.y instead of walking them one after the other
+    const long long gy = a.num_tiles < slots ? std::min<long long>(a.d_out, (slots + a.num_tiles - 1) / a.num_tiles) : 1;
+    const size_t smem = lean_smem_bytes(d, NW, DEEP);
+    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_lean_kernel");
     return SMX_OK;
 }
 template <int NW>
 int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
+    if (d.deep) return d.eta0_zero ? launch_lean2<NW, true, false, true, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, true>(map, a, d, x, y, st);
     static const int elect = std::getenv("SMX_FAST_ELECT") ? std::atoi(std::getenv("SMX_FAST_ELECT")) : 1;  // tuning knob (measured: 1.847 vs 1.888 ms)
-    if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true>(map, a, d, x, y, st);
-    return d.eta0_zero ? launch_lean2<NW, true, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false>(map, a, d, x, y, st);
+    if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false>(map, a, d, x, y, st);
+    return d.eta0_zero ? launch_lean2<NW, true, false, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false, false>(map, a, d, x, y, st);
 }
 
 }  // namespace
@@ -709,6 +740,21 @@ int fast_kernel_prepare(FastDevice& d) {
             }
         }
     }
+    // hot parts of five to eight pairs: the lean kernel with eight-factor records (values only; the gradient then runs on the
+    // per-summand kernels).  Chosen when no variant with product rows fits in shared memory (SMX_FAST_DEEP=1: always).
+    d.deep = false;
+    if (!d.flat_ok && d.deep_ok && want_flat) {
+        static const int want_deep = std::getenv("SMX_FAST_DEEP") ? std::atoi(std::getenv("SMX_FAST_DEEP")) : -1;
+        if (want_deep == 1 || (want_deep != 0 && !(fits4 || fits8 || fits12 || fits16))) {
+            for (int nw : {8, 6}) {
+                if (2 * (lean_smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) {
+                    d.flat = d.deep = true;
+                    d.warps = nw;
+                    return SMX_OK;
+                }
+            }
+        }
+    }
     d.warps = 0;
     if (want == 16 && fits16) d.warps = 16;
     else if (want == 12 && fits12) d.warps = 12;
@@ -745,12 +791,14 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
     if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
     if (d.flat) {
+        if (a.gradient && d.deep) return fail(SMX_ERR_UNSUPPORTED, "eight-factor records: the fast path has no gradient kernel for them");
         if (a.gradient && d.warps == 7) return fail(SMX_ERR_UNSUPPORTED, "7 warps per CTA: lean kernel only (tuning knob)");
         if (a.gradient && d.warps == 12) return launch<12, 1, 0, true, 2, true>(map, a, d, x, y, st);
         if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
         // values: the lean item loop (SMX_FAST_LEAN=0 selects the general kernel, for A/B timing)
         static const int lean = std::getenv("SMX_FAST_LEAN") ? std::atoi(std::getenv("SMX_FAST_LEAN")) : 1;
-        if (lean && a.N < (1ll << 31) - kTile) {
+        if (d.deep && a.N >= (1ll << 31) - kTile) return fail(SMX_ERR_UNSUPPORTED, "more than 2^31 points in one call");
+        if ((lean || d.deep) && a.N < (1ll << 31) - kTile) {
             if (d.warps == 8) return launch_lean<8>(map, a, d, x, y, st);
             if (d.warps == 7) return launch_lean<7>(map, a, d, x, y, st);
             if (d.warps == 6) return launch_lean<6>(map, a, d, x, y, st);

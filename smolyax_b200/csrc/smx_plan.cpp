@@ -566,6 +566,9 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             if (l <= 4) {  // rows of up to four pairs are also stored as a flat product of hot rows (one pass, no level order)
                 for (int f = 0; f < 4; ++f) plan.tab_factors.push_back(f < l ? hot_tab.at(row_key[r][f]) : 0);
             }
+            if (l <= 8) {  // .. and every row of up to eight pairs with its full factor list (kernels without product rows)
+                for (int f = 0; f < 8; ++f) plan.tab_factors8.push_back(f < l ? hot_tab.at(row_key[r][f]) : 0);
+            }
         }
         plan.level_off[l + 1] = next;
     }
@@ -741,6 +744,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     // ---- 10. kernel-side packing: directory + one contiguous metadata record per work item ------------------------
     plan.chunk_dir.resize((size_t)plan.n_chunks * 4);
     plan.chunk_meta.assign((size_t)plan.n_chunks * kMetaInts, 0);
+    plan.chunk_fac2.assign((size_t)plan.n_chunks * 64, 0);
     plan.chunk_kmask.assign((size_t)plan.n_chunks, 0);
     plan.padded_fma = 0;
     for (int32_t c = 0; c < plan.n_chunks; ++c) {
@@ -762,6 +766,8 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         // product rows in the value table multiplies them on the fly.  nf = most factors of any row of the item.
         int32_t nf = 1;
         const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
+        const int32_t n_flat8 = (int32_t)(plan.tab_factors8.size() / 8);
+        int32_t* fac2 = &plan.chunk_fac2[(size_t)c * 64];
         for (int32_t i = 0; i < kBlockWidth; ++i) {
             int32_t* f4 = meta + 96 + 4 * i;
             const int32_t row = i < rows ? plan.chunk_rows[r0 + i] : 0;
@@ -775,7 +781,18 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                 }
                 nf = std::max(nf, cnt);
             } else {
-                plan.flat_ok = false;  // a hot part of five or more pairs: only the variant with product rows can run
+                plan.flat_ok = false;  // a hot part of five or more pairs: the four-factor kernels cannot run ..
+                if (row - flat_begin < n_flat8) {  // .. the eight-factor ("deep") one can: factors 5..8 go to a second list
+                    int32_t cnt = 0;
+                    for (int f = 0; f < 8; ++f) {
+                        const int32_t v = plan.tab_factors8[(size_t)(row - flat_begin) * 8 + f];
+                        (f < 4 ? f4[f] : fac2[4 * i + f - 4]) = v;
+                        if (v != 0) cnt = f + 1;
+                    }
+                    nf = std::max(nf, cnt);
+                } else {
+                    plan.deep_ok = false;
+                }
             }
         }
         bool eta_zero = !(plan.chunk_flags[c] & kChunkHot);

@@ -127,6 +127,9 @@ struct FastPlan {
     std::vector<int32_t> chunk_dir;      // 4 ints per item: first row slot, number of rows, flags | nf << 8 (nf = most hot
                                          // factors of any of its rows), first column of x
     bool flat_ok = true;                 // every row is a product of at most four hot rows (factor lists in the metadata)
+    bool deep_ok = true;                 // .. of at most eight: the "deep" records carry a second factor list per row slot
+    std::vector<int32_t> tab_factors8;   // 8 ints per row of level 2..8: its hot rows (0 = the ones row)
+    std::vector<int32_t> chunk_fac2;     // 64 ints per item: factors 5..8 of row slot i at [4 * i .. 4 * i + 3] (0 = ones row)
     std::vector<int32_t> chunk_kmask;    // bit 2 s + j set: k-step s has a non-zero coefficient in entries 8 j .. 8 j + 7
     std::vector<int32_t> chunk_meta;     // kMetaInts ints per item: tab[16], deg[16], eta offset[16], row index[16], eta0[16]
                                          // (doubles), then per row slot the four hot rows whose product it is (int4)

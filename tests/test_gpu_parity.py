@@ -300,3 +300,40 @@ def test_few_outputs_multi_set_kernel(d_in, d_out, n_target, rule):
     J_orc = oracle.gradient(ip.reference_layout(), x[:16])
     ok = ~np.isnan(J_orc)
     assert np.array_equal(np.isnan(J), np.isnan(J_orc)) and np.max(np.abs(J[ok] - J_orc[ok])) <= 1e-9 * max(1.0, float(np.max(np.abs(J_orc[ok]))))
+
+
+def _benchmark_grid_interpolator(d_in, d_out, n_target, **extra):
+    """A cell of the reference's heat-map grid (benchmarking/benchmark.py:33-36,180): k_j = log((j + 2)^r / theta)."""
+    from smolyax_b200 import indices, nodes, workloads
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    k = np.array([np.log(((j + 2) ** workloads.BASE_R) / workloads.BASE_THETA) for j in range(d_in)])
+    gen = nodes.Leja(dim=d_in)
+    t = indices.find_approximate_threshold(k, n_target, gen.is_nested)
+    f = workloads.TargetFamily(d_in, d_out)
+    return f, SmolyakBarycentricInterpolator(node_gen=gen, k=k, t=t, d_out=d_out, f=f, batched_f=True, **extra)
+
+
+@pytest.mark.parametrize("layout", ["reference", "compact"])
+@pytest.mark.parametrize("d_out", [1, 3, 40])
+def test_values_low_dimensional_high_cardinality(d_out, layout):
+    """d_in = 10, |Lambda| = 6000 (reference benchmark grid): terms with up to seven active dimensions, i.e. hot parts of
+    five and six pairs, and a product table far beyond shared memory.  Must stay on the fast path (eight-factor records),
+    for any d_out (the GEMM-regime kernel needs the product table, so d_out = 40 runs the block-sparse kernel too)."""
+    from oracle import oracle
+
+    f, ip = _benchmark_grid_interpolator(10, d_out, 6000, layout=layout)
+    info = ip.device_info()
+    assert info["has_fast_path"] == 1
+    x = np.random.default_rng(5).uniform(-1.0, 1.0, size=(777, 10))
+    y = ip(x)
+    # the oracle needs the reference layout: assemble it separately for the compact handle
+    _, ip_ref = (f, ip) if layout == "reference" else _benchmark_grid_interpolator(10, d_out, 6000, layout="reference",
+                                                                                   method="barycentric")
+    ref_layout = ip_ref.reference_layout()
+    y_orc = oracle.evaluate(ref_layout, x)
+    # summand magnitude sum_nu |zeta_nu I_nu f| is O(sum |zeta|) * |f| here; the fast path is far more accurate than the
+    # reference arithmetic, so compare against f as well (the interpolation error at 6000 nodes is ~1e-9)
+    assert np.max(np.abs(y - y_orc)) < 1e-10 * max(1.0, np.max(np.abs(y_orc)))
+    assert np.sqrt(np.mean((y - f(x)) ** 2) / np.mean(f(x) ** 2)) < 1e-7
+    assert np.array_equal(ip(torch.from_numpy(x).cuda()).cpu().numpy(), y)
