@@ -380,7 +380,7 @@ __device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* 
     if (cold) tma_load_2d(xs, xmap, dir.w, p0, b);
 }
 
-template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP = false>
+template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP = false, bool ONE = false>
 __global__ void __launch_bounds__(NW * 32, 2)
 fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -467,9 +467,9 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         __syncthreads();
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);
 
-        const int n_out = (int)a.d_out;
+        const int n_out = ONE ? 1 : (int)a.d_out;  // ONE: single output, the set offset folds away in the staging code
         // (outputs are spread over gridDim.y when there are fewer tiles than CTA slots: small batches, many outputs)
-        for (int o = blockIdx.y; o < n_out; o += gridDim.y) {
+        for (int o = ONE ? 0 : (int)blockIdx.y; o < n_out; o += ONE ? 1 : (int)gridDim.y) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             int4 dir = make_int4(0, 0, 0, 0);
             const int4* dp = dir_begin;
@@ -638,7 +638,7 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
                 y[((long long)p0 + tid) * a.d_out + o] = s;
             }
-            if (o + (int)gridDim.y < n_out) __syncthreads();
+            if (!ONE && o + (int)gridDim.y < n_out) __syncthreads();
         }
     }
 }
@@ -682,20 +682,22 @@ size_t lean_smem_bytes(const FastDevice& d, int nw, bool deep) {
     return smem_bytes(d, nw, true) + (deep ? (size_t)nw * (lean_stage_bytes<true>() - lean_stage_bytes<false>()) : 0);
 }
 
-template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP>
+template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP, bool ONE = false>
 int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long slots = (long long)d.sm_count * 2, grid = std::min<long long>(a.num_tiles, slots);
     // fewer tiles than CTA slots: split the outputs over gridDim.y instead of walking them one after the other
     const long long gy = a.num_tiles < slots ? std::min<long long>(a.d_out, (slots + a.num_tiles - 1) / a.num_tiles) : 1;
     const size_t smem = lean_smem_bytes(d, NW, DEEP);
-    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, y);
+    SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_lean_kernel");
     return SMX_OK;
 }
 template <int NW>
 int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     if (d.deep) return d.eta0_zero ? launch_lean2<NW, true, false, true, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, true>(map, a, d, x, y, st);
+    static const int one = std::getenv("SMX_FAST_ONE") ? std::atoi(std::getenv("SMX_FAST_ONE")) : 1;  // tuning knob
+    if (one && a.d_out == 1) return d.eta0_zero ? launch_lean2<NW, true, false, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false, true>(map, a, d, x, y, st);
     static const int elect = std::getenv("SMX_FAST_ELECT") ? std::atoi(std::getenv("SMX_FAST_ELECT")) : 1;  // tuning knob (measured: 1.847 vs 1.888 ms)
     if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false>(map, a, d, x, y, st);
     return d.eta0_zero ? launch_lean2<NW, true, false, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false, false>(map, a, d, x, y, st);
