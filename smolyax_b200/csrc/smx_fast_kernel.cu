@@ -787,8 +787,13 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     const cuuint64_t strides[1] = {(cuuint64_t)a.ldx * sizeof(double)};
     const cuuint32_t box[2] = {kBlockWidth, kTile};
     const cuuint32_t estr[2] = {1, 1};
+    // L2 promotion: a tile row is 128 bytes; with 256-byte promotion the fetch also brings the same rows of the next column
+    // block into L2 (another item of the same tile, a few microseconds later)
+    static const int promo = std::getenv("SMX_FAST_L2PROMO") ? std::atoi(std::getenv("SMX_FAST_L2PROMO")) : 256;  // (measured: 1.790 vs 1.799 ms)
     const CUresult res = encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                        : promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
     if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
