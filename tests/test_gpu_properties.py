@@ -248,3 +248,54 @@ def test_compact_create_rejects_malformed_descriptors_and_flags():
     # SMX_NO_DENSE_PATH / SMX_DENSE_PATH are honoured
     assert _lib.info(_lib.create_compact(good, 6, 3, _lib.SMX_DENSE_PATH))["has_dense_path"] == 1
     assert _lib.info(_lib.create_compact(good, 6, 3, _lib.SMX_NO_DENSE_PATH))["has_dense_path"] == 0
+
+
+def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
+    """The lean block-sparse kernel: (a) a small batch spreads its outputs over gridDim.y, a large one walks them inside
+    the CTA - same bits either way; (b) the general kernel (SMX_FAST_LEAN=0, read once per process, so in a child
+    process) gives the same bits as the lean one; (c) non-zero first centres (custom Leja domain) take the variant
+    with the subtraction and still reproduce a polynomial exactly."""
+    import os
+    import subprocess
+    import sys
+
+    d_in, d_out = 24, 10  # below the GEMM regime: ten passes of the block-sparse kernel
+    k = workloads.anisotropy(d_in)
+    gen = nodes.Leja(dim=d_in)
+    t = indices.find_approximate_threshold(k, 700, True)
+    f = workloads.TargetFamily(d_in, d_out)
+    ip = _interp(node_gen=gen, k=k, t=t, d_out=d_out, f=f, batched_f=True)
+    assert ip.device_info()["has_fast_path"] == 1 and ip.device_info()["has_dense_path"] == 0
+    x = torch.rand((40_000, d_in), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 2 - 1
+    y_big = ip(x)                      # 1250 tiles: gridDim.y = 1
+    y_small = ip(x[:1000])             # 32 tiles: outputs spread over gridDim.y
+    assert torch.equal(y_small, y_big[:1000])
+    assert torch.equal(ip(x[:33]), y_big[:33])
+    np.save("/tmp/_smx_knob_x.npy", x[:4096].cpu().numpy())
+    np.save("/tmp/_smx_knob_y.npy", y_big[:4096].cpu().numpy())
+    child = (
+        "import numpy as np, torch\n"
+        "from smolyax_b200 import indices, nodes, workloads\n"
+        "from smolyax_b200.interpolation import SmolyakBarycentricInterpolator\n"
+        f"d_in, d_out = {d_in}, {d_out}\n"
+        "k = workloads.anisotropy(d_in)\n"
+        "t = indices.find_approximate_threshold(k, 700, True)\n"
+        "ip = SmolyakBarycentricInterpolator(node_gen=nodes.Leja(dim=d_in), k=k, t=t, d_out=d_out,\n"
+        "                                    f=workloads.TargetFamily(d_in, d_out), batched_f=True)\n"
+        "y = ip(torch.from_numpy(np.load('/tmp/_smx_knob_x.npy')).cuda()).cpu().numpy()\n"
+        "assert np.array_equal(y, np.load('/tmp/_smx_knob_y.npy')), np.max(np.abs(y - np.load('/tmp/_smx_knob_y.npy')))\n"
+    )
+    env = dict(os.environ, SMX_FAST_LEAN="0", PYTHONPATH=os.pathsep.join([os.getcwd()] + sys.path))
+    out = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+
+    # (c) custom domain: first centres != 0
+    rng = np.random.default_rng(11)
+    dom = np.stack([rng.uniform(-3, -1, 6), rng.uniform(0.5, 2, 6)], axis=1)
+    gen_c = nodes.Leja(domains=dom)
+    k_c = workloads.anisotropy(6)
+    t_c = indices.find_approximate_threshold(k_c, 200, True)
+    fp = ProductPolynomial(gen_c, k_c, t_c, 3, rng)
+    ip_c = _interp(node_gen=gen_c, k=k_c, t=t_c, d_out=3, f=fp)
+    xc = rng.uniform(dom[:, 0], dom[:, 1], size=(500, 6))
+    assert np.allclose(ip_c(xc), fp(xc), rtol=1e-9, atol=1e-9)
