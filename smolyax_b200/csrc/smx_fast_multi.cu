@@ -258,7 +258,10 @@ bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* war
     static const int want = std::getenv("SMX_FAST_MULTI") ? std::atoi(std::getenv("SMX_FAST_MULTI")) : -1;  // 0: off; 2, 3: force
     if (want == 0 || !d.flat_ok || d.d_out < 2 || d.d_out >= 32) return false;
     if (want < 0 && d.d_out > 6) return false;
-    const int s = want > 0 ? want : ((d.d_out == 2 || d.d_out == 4) ? 2 : 3);
+    // (measured against one output per pass of the lean kernel, cfg2 tables, ms per 1e6 points: 2 outputs 3.46 vs 3.29,
+    //  3: 4.57 vs 4.75, 4: 6.52 vs 6.21, 6: 8.74 vs 9.13 - three sets per pass still pay, two no longer do)
+    if (want < 0 && (d.d_out == 2 || d.d_out == 4)) return false;
+    const int s = want > 0 ? want : 3;
     if (s == 2 && multi_smem_bytes<2>(d, 12) <= (size_t)smem_optin) return *sets = 2, *warps = 12, true;
     if (s == 3 && multi_smem_bytes<3>(d, 8) <= (size_t)smem_optin) return *sets = 3, *warps = 8, true;
     return false;

@@ -132,8 +132,9 @@ class SmolyakBarycentricInterpolator:
 
     def _release(self):
         handle, self._handle = getattr(self, "_handle", None), None
-        if handle is not None and _lib is not None:
-            _lib.lib.smx_destroy(handle)
+        lib = getattr(_lib, "lib", None) if _lib is not None else None  # (module globals are torn down at interpreter exit)
+        if handle is not None and lib is not None:
+            lib.smx_destroy(handle)
 
     # ------------------------------------------------------------------ set_f (interpolation.py:115-239)
     def set_f(self, *, f: Callable, f_evals: dict = None) -> dict:
