@@ -18,6 +18,8 @@ SMX_GRAD_FINITE_AT_NODES = 4
 SMX_DENSE_PATH = 8
 SMX_NO_DENSE_PATH = 16
 
+SMX_ERR_UNSUPPORTED = 4
+
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "out of device memory", 4: "unsupported shape", 5: "no sm_100 device"}
 
 

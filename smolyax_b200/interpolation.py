@@ -25,6 +25,7 @@ import torch
 from . import _lib, indices, nodes  # noqa: F401
 
 _CODE = 1 << 20  # (dim, deg) -> dim * _CODE + deg
+_GRAD_COLUMN_BLOCK = 1024  # outputs per set of derivative tables when one handle cannot hold them for every output
 
 
 def _host_weights(pts: np.ndarray) -> np.ndarray:
@@ -442,11 +443,29 @@ class SmolyakBarycentricInterpolator:
         with torch.cuda.device(self._device):
             xd = x if kind == "cuda" else (x.cuda() if kind == "torch_cpu" else torch.from_numpy(x).cuda())
             J = torch.empty((n_points, self._d_out, self._d_in), dtype=torch.float64, device=xd.device)
-            _lib.check(_lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, self._ldx(xd), J.data_ptr(), self._stream()),
-                       "smx_gradient")
+            status = _lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, self._ldx(xd), J.data_ptr(), self._stream())
+            if status == _lib.SMX_ERR_UNSUPPORTED and self._layout.get("compact") and self._d_out > _GRAD_COLUMN_BLOCK:
+                self._gradient_by_columns(xd, J)  # derivative sets of all outputs at once were not built (d_out too large)
+            else:
+                _lib.check(status, "smx_gradient")
             if kind == "cuda":
                 return J
             return J.cpu() if kind == "torch_cpu" else J.cpu().numpy()
+
+    def _gradient_by_columns(self, xd, J) -> None:
+        """Gradient of a handle too wide for one set of derivative tables (compact layout, ``d_out`` in the thousands):
+        the interpolant is linear in ``f``, so ``J[:, lo:hi, :]`` is the gradient of the interpolant of outputs
+        ``lo:hi`` alone.  One temporary handle per block of ``_GRAD_COLUMN_BLOCK`` outputs (its derivative sets are
+        built, used once and freed: the tables of all blocks together are what did not fit)."""
+        from .dist import column_slice
+
+        for lo in range(0, self._d_out, _GRAD_COLUMN_BLOCK):
+            hi = min(lo + _GRAD_COLUMN_BLOCK, self._d_out)
+            block = SmolyakBarycentricInterpolator(node_gen=self._node_gen, k=self._k, t=self._t, d_out=hi - lo,
+                                                   device=self._device, nan_at_nodes=self._nan_at_nodes, layout="compact")
+            block.set_layout(column_slice(self._layout, lo, hi))
+            J[:, lo:hi, :] = block.gradient(xd)
+            block._release()
 
     # ------------------------------------------------------------------ integral (interpolation.py:347-390)
     def integral(self):
