@@ -337,3 +337,29 @@ def test_values_low_dimensional_high_cardinality(d_out, layout):
     assert np.max(np.abs(y - y_orc)) < 1e-10 * max(1.0, np.max(np.abs(y_orc)))
     assert np.sqrt(np.mean((y - f(x)) ** 2) / np.mean(f(x) ** 2)) < 1e-7
     assert np.array_equal(ip(torch.from_numpy(x).cuda()).cpu().numpy(), y)
+
+
+def test_gradient_wider_than_one_set_of_derivative_tables():
+    """d_out > 2 048 on the compact layout: the handle keeps only the GEMM-regime value tables, ``smx_gradient`` answers
+    SMX_ERR_UNSUPPORTED and ``gradient`` works through blocks of output columns (linearity in f).  Checked against the
+    per-summand kernels on the reference layout (which are checked against the oracle above)."""
+    from smolyax_b200 import _lib, workloads
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    d_in, d_out = 4, 2056  # (four dimensions: no hot part deeper than four pairs)
+    w = workloads.Workload("wide_grad", "leja", d_in, d_out, 60, 0)
+    ip = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(), layout="compact")
+    x = w.points(37, seed=3)
+    xt = torch.from_numpy(x).cuda()
+    J_raw = torch.empty((len(x), d_out, d_in), dtype=torch.float64, device="cuda")
+    status = _lib.lib.smx_gradient(ip._handle, xt.data_ptr(), len(x), d_in, J_raw.data_ptr(), None)
+    assert status == _lib.SMX_ERR_UNSUPPORTED  # (the C ABI itself still says so: the blocks are the host layer's)
+    J = ip.gradient(x)
+    assert J.shape == (len(x), d_out, d_in)
+    ref = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(),
+                                         layout="reference", method="barycentric")
+    J_ref = ref.gradient(x)
+    scale = max(1.0, float(np.nanmax(np.abs(J_ref))))
+    assert np.array_equal(np.isnan(J), np.isnan(J_ref))
+    assert np.max(np.abs(np.nan_to_num(J) - np.nan_to_num(J_ref))) <= 1e-9 * scale  # (the bound of test_gradient)
+    assert np.allclose(ip.gradient(xt).cpu().numpy(), J, rtol=0, atol=1e-12 * scale, equal_nan=True)  # device input
