@@ -5,7 +5,7 @@
 namespace smx {
 
 constexpr int kDenseTile = 32;  // points per CTA
-static_assert(kDenseStageK4 == 16 && kDensePadK4 == 64, "stages of 8 or 16 k-steps; look-ahead of up to 3 x 16 k-steps");
+static_assert(kDenseStageK4 == 16 && kDensePadK4 == 64, "stages of 8 or 16 k-steps; look-ahead of up to 3 x 16 k-steps (meta: stage s + 3)");
 
 struct DenseArgs {
     const double* eta;
@@ -23,6 +23,7 @@ struct DenseArgs {
     int k4;                  // k-steps (4 terms each), a multiple of kDenseStageK4; arrays carry kDensePadK4 more (zeros)
     int nblk;                // ceil(ncol / 8)
     int n_tab, n_hot_rows, n_levels, hot_dims;
+    int skew;                // staged kernel: half of the warps assemble A before their DMMAs (set by dense_kernel_launch)
     int level_off[kMaxLevels + 2];
 };
 

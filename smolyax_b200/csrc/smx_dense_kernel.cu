@@ -117,10 +117,22 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
         dst[32] = make_double2(v[2], v[3]);
     };
 
+    // Skewed stages (a.skew): the warps of the upper half of every group of eight assemble their k-step of stage s + 1
+    // BEFORE the DMMAs of stage s (from coordinates they requested a stage earlier), the others after them - so between
+    // two stage barriers half of the CTA is always in its DMMA phase and the FP64 pipe does not drain while everybody
+    // builds fragments at the same time.  Both orders respect the two-buffer protocol: buffer (s + 1) & 1 was last read
+    // in stage s - 1, and it is complete at the barrier that ends stage s.
+    // Measured (B200, ms per 10^6 points): cfg5 (13 blocks, 8 warps x 2 blocks) 82.6 -> 78.1; no gain for the 16-warp x 4-block
+    // shape (cfg3: 611 vs 614), which waits for the pipe and for nothing else and has no registers to spare for the deeper
+    // metadata look-ahead - compiled out there.
+    constexpr bool kSkew = NB < 4;
+    const bool early = kSkew && a.skew != 0 && ((warp >> 2) & 1) != 0;
     int2 m1 = meta_of(0);
     load_cold(m1);
     assemble(m1, 0);
     m1 = meta_of(1);
+    int2 m2 = kSkew ? meta_of(2) : m1;
+    if (early) load_cold(m1);
     __syncthreads();
 
     double acc[4][NB][2];
@@ -158,12 +170,18 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     };
 
     for (int s = 0; s < n_stage; ++s) {
-        const int2 m2 = meta_of(s + 2);
-        load_cold(m1);  // for stage s + 1; consumed after the DMMAs below
+        const int2 mn = meta_of(s + (kSkew ? 3 : 2));
+        if (early) {
+            assemble(m1, (s + 1) & 1);
+            load_cold(m2);  // for stage s + 2: consumed at the start of the next iteration
+        } else {
+            load_cold(m1);  // for stage s + 1; consumed after the DMMAs below
+        }
         if (nbv == NB) stage_mma(s, std::true_type());
         else if (nbv > 0) stage_mma(s, std::false_type());
-        assemble(m1, (s + 1) & 1);
-        m1 = m2;
+        if (!early) assemble(m1, (s + 1) & 1);
+        if (kSkew) m1 = m2, m2 = mn;
+        else m1 = mn;
         __syncthreads();
     }
 
@@ -369,10 +387,13 @@ bool dense_kernel_fits(int n_tab, int smem_optin) { return dense_smem_bytes(n_ta
 // CTA shape.  Many outputs: 16 warps x 4 output blocks (32 points x 512 outputs per CTA; the widest register tile, fewest
 // A-fragment loads per DMMA).  Few outputs: 8 warps x 1 or 2 blocks with a deeper B ring, two CTAs per SM when the value
 // table leaves room (more independent DMMA chains and loads in flight per SM).
-int dense_kernel_launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
+int dense_kernel_launch(const DenseArgs& args, const double* x, double* y, cudaStream_t st) {
     static const int want_nb = std::getenv("SMX_DENSE_NB") ? std::atoi(std::getenv("SMX_DENSE_NB")) : 0;
     static const int want_nw = std::getenv("SMX_DENSE_NW") ? std::atoi(std::getenv("SMX_DENSE_NW")) : 0;
     static const int want_ctas = std::getenv("SMX_DENSE_CTAS") ? std::atoi(std::getenv("SMX_DENSE_CTAS")) : 0;
+    static const int want_skew = std::getenv("SMX_DENSE_SKEW") ? std::atoi(std::getenv("SMX_DENSE_SKEW")) : 1;
+    DenseArgs a = args;
+    a.skew = want_skew;
     int device = 0, smem_sm = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));

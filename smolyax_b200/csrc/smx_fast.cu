@@ -297,6 +297,7 @@ int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.n_hot_rows = d.n_hot_rows;
     a.n_levels = d.n_levels;
     a.hot_dims = d.hot_dims;
+    a.skew = 0;  // (dense_kernel_launch decides)
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
     return dense_kernel_launch(a, x, out, st);
 }
