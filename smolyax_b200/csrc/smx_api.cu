@@ -357,6 +357,15 @@ int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, d
         // per 8 GB at cfg2, i.e. the PCIe link - 54 GB/s - whatever the chunk)
         static const long long chunk_mb = std::getenv("SMX_HOST_CHUNK_MB") ? std::atoll(std::getenv("SMX_HOST_CHUNK_MB")) : 32;
         chunk_points = std::max<int64_t>(1024, (chunk_mb << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
+        // whole waves of 32-point tiles (two CTAs per SM; the GEMM-regime kernel runs ceil(d_out / 128 .. 512) CTAs per tile):
+        // a chunk that fills 44 % of the CTA slots takes as long as a full one.  It does not matter while the link is the
+        // bound (cfg2), it does when the kernel is (cfg5, 32 MiB = 4 194 points = 131 of 296 slots: 467 ms per 10^6 points
+        // end to end against 78 ms of kernel time and 150 ms of copies)
+        if (h->has_fast && h->fast.sm_count > 0) {
+            const int64_t per_tile = h->d_out >= 384 ? (h->d_out + 511) / 512 : (h->d_out + 127) / 128;
+            const int64_t wave = std::max<int64_t>(1, ((int64_t)h->fast.sm_count * 2 + per_tile - 1) / per_tile) * 32;
+            chunk_points = (chunk_points + wave - 1) / wave * wave;
+        }
     }
     chunk_points = std::min(chunk_points, N);
     int rc;

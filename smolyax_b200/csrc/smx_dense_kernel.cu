@@ -406,9 +406,14 @@ int dense_kernel_launch(const DenseArgs& args, const double* x, double* y, cudaS
         if (per <= 4) return launch_splitk<16, 4>(a, x, y, st);
         return launch_splitk<8, 8>(a, x, y, st);
     }
-    const int nb = want_nb ? want_nb : (a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1);
-    const int nw = want_nw ? want_nw : (nb == 4 ? 16 : 8);
     const bool two_fit = 2 * (dense_smem_bytes(a.n_tab, 8) + 1024) <= (size_t)smem_sm;
+    int nb = a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1, nw = nb == 4 ? 16 : 8;
+    // a value table too large for two CTAs of 8 warps per SM (many hot rows, e.g. cfg3's tables): one CTA of 16 warps, one
+    // block per warp up to 24 blocks (measured, fraction of the DMMA rate at 13 / 20 / 40 blocks: 8 warps x 2 blocks
+    // 0.59 / 0.58 / 0.72, 16 x 1: 0.62 / 0.71 / 0.79, 16 x 2: 0.57 / 0.69 / 0.80)
+    if (nb < 4 && !two_fit) nw = 16, nb = a.nblk <= 24 ? 1 : 2;
+    if (want_nb) nb = want_nb;
+    if (want_nw) nw = want_nw;
     const int ctas = want_ctas ? want_ctas : (two_fit ? 2 : 1);
     if (nb == 4) return nw <= 8 ? launch<8, 4, 4, 1>(a, x, y, st) : launch<16, 4, 2, 1>(a, x, y, st);
     if (nb == 2) {

@@ -411,26 +411,35 @@ class SmolyakBarycentricInterpolator:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ __call__ (interpolation.py:264-304)
-    def __call__(self, x):
+    def __call__(self, x, out=None):
         """Evaluate the interpolant at ``x`` of shape ``(n_points, d_in)`` or ``(d_in,)``; result ``(n_points, d_out)``.
 
         A CUDA ``torch`` tensor is evaluated in place on the current stream and a CUDA tensor is returned without
         synchronising (like the reference's un-synchronised ``jax.Array``).  Host input (NumPy, or a CPU tensor —
         pinned for full speed) goes through the pipelined host path and returns a host array of the same kind.
+
+        ``out`` (not in the reference): a C-contiguous float64 buffer of shape ``(n_points, d_out)`` of the same kind as
+        ``x`` to write the result into.  Worth it for wide outputs from host memory: a fresh page-locked result buffer
+        costs about a second per 8 GB, more than the evaluation.
         """
         x, kind = self._validate_input(x)
         n_points = x.shape[0]
         lib = _lib.lib
+        if out is not None:
+            ok = (isinstance(out, torch.Tensor) and out.dtype == torch.float64 and out.is_contiguous() and
+                  (out.is_cuda and out.device == x.device if kind == "cuda" else not out.is_cuda)) if kind != "numpy" else \
+                 (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.flags.writeable)
+            assert ok and tuple(out.shape) == (n_points, self._d_out), "out: C-contiguous float64 (n_points, d_out) of the same kind as x"
         with torch.cuda.device(self._device):
             if kind == "cuda":
-                y = torch.empty((n_points, self._d_out), dtype=torch.float64, device=x.device)
+                y = torch.empty((n_points, self._d_out), dtype=torch.float64, device=x.device) if out is None else out
                 _lib.check(lib.smx_eval(self._handle, x.data_ptr(), n_points, self._ldx(x), y.data_ptr(), self._stream()), "smx_eval")
                 return y
             if kind == "torch_cpu":
-                y = torch.empty((n_points, self._d_out), dtype=torch.float64, pin_memory=x.is_pinned())
+                y = torch.empty((n_points, self._d_out), dtype=torch.float64, pin_memory=x.is_pinned()) if out is None else out
                 _lib.check(lib.smx_eval_host(self._handle, x.data_ptr(), n_points, self._ldx(x), y.data_ptr(), 0), "smx_eval_host")
                 return y
-            y = np.empty((n_points, self._d_out))
+            y = np.empty((n_points, self._d_out)) if out is None else out
             _lib.check(lib.smx_eval_host(self._handle, x.ctypes.data, n_points, x.shape[1], y.ctypes.data, 0), "smx_eval_host")
             return y
 

@@ -299,3 +299,28 @@ def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
     ip_c = _interp(node_gen=gen_c, k=k_c, t=t_c, d_out=3, f=fp)
     xc = rng.uniform(dom[:, 0], dom[:, 1], size=(500, 6))
     assert np.allclose(ip_c(xc), fp(xc), rtol=1e-9, atol=1e-9)
+
+
+def test_out_buffer_of_each_input_kind():
+    """``__call__(x, out=...)``: the caller's result buffer (device, page-locked host, NumPy) receives the same bits as a
+    fresh one; a buffer of the wrong shape, type or kind is refused like any other bad argument (AssertionError)."""
+    from smolyax_b200 import workloads
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    w = workloads.Workload("out", "leja", 12, 3, 200, 0)
+    ip = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=3, f=w.target())
+    x = w.points(1000, seed=11)
+    y = ip(x)
+    out_np = np.full((1000, 3), np.nan)
+    assert ip(x, out=out_np) is out_np and np.array_equal(out_np, y)
+    xt = torch.from_numpy(x).cuda()
+    out_dev = torch.full((1000, 3), float("nan"), dtype=torch.float64, device="cuda")
+    assert ip(xt, out=out_dev) is out_dev and np.array_equal(out_dev.cpu().numpy(), y)
+    xp = torch.from_numpy(x).pin_memory()
+    out_pin = torch.full((1000, 3), float("nan"), dtype=torch.float64).pin_memory()
+    assert ip(xp, out=out_pin) is out_pin and np.array_equal(out_pin.numpy(), y)
+    for bad in (np.empty((999, 3)), np.empty((1000, 3), dtype=np.float32), np.empty((3, 1000)).T, out_dev):
+        with pytest.raises(AssertionError):
+            ip(x, out=bad)
+    with pytest.raises(AssertionError):
+        ip(xt, out=out_pin)
