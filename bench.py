@@ -311,7 +311,11 @@ def main():
                     f"needs {2.0 * fma_per_eval * d_loc * n_points / ((fp64_peak or 37.12) * 1e12) * 1e3:.2f} ms per launch at the measured DMMA peak, "
                     f"the x stream {alg_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3:.2f} ms at the measured HBM peak",
         }
-        if dense:
+        # which roof: SURVEY 8(d) t_roof = max(bytes / BW, flops / FP64 rate), with the folded form's 2 * n_terms * d_out
+        # flops per point (the fewest any polynomial evaluation of this interpolant needs; padding is not counted)
+        fp64_bound = (not dense and fp64_peak and
+                      2.0 * info["n_terms"] * d_loc * n_points / (fp64_peak * 1e12) > alg_bytes / (peaks["hbm_gbs"] * 1e9))
+        if dense or fp64_bound:
             # GEMM regime (folded form): algorithmic flops = 2 * d_out * n_terms per point, on the FP64 tensor
             # instruction; the denominator is the FP64 DMMA rate measured on this GPU type (profiles/fp64_peaks.json) -
             # MEASURED_PEAKS.json only carries the bf16 tensor rate, which no fp64 path can use.
@@ -320,9 +324,14 @@ def main():
             roofline = {
                 "bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
                 "traffic": traffic, "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) rate measured with profiles/fp64_peaks.cu",
-                "kernel": "dense_eval_kernel", "algorithmic_flops_per_launch": alg_flops,
+                "kernel": "dense_eval_kernel" if dense else roofline["kernel"], "algorithmic_flops_per_launch": alg_flops,
                 "hbm_gbs_algorithmic": achieved, "hbm_peak_gbs": peaks["hbm_gbs"],
             }
+            if not dense:
+                roofline["fp64_tflops_executed"] = fp64_tflops  # block-sparse form incl. its padding (2 * padded_fma per point and output)
+                roofline["launches_per_step"] = launches // max(args.steps, 1)
+                if ms_per_step < 0.2:
+                    roofline["note"] = "a step of this size is launch/latency-bound (tens of microseconds per call), not pipe-bound"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns else "weak", "vs_baseline": None,
