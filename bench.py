@@ -189,6 +189,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
+        # (NCCL prints its version banner to stdout when NCCL_DEBUG is set: keep stdout to the one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = workloads.CONFIGS[args.config]
