@@ -30,6 +30,22 @@ METRIC = "interpolant evals/sec (points*d_out/s) at d_in=1e3,n=1e4"
 UNIT = "points*d_out/s"
 
 
+_RESULT_STREAM = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: whatever a library prints to file descriptor 1 during the run
+    (NCCL's version banner when NCCL_DEBUG is set, as on the GPU boxes) is sent to stderr instead."""
+    global _RESULT_STREAM
+    sys.stdout.flush()
+    _RESULT_STREAM = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    print(json.dumps(line), file=_RESULT_STREAM or sys.stdout, flush=True)
+
+
 def measured_peaks():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
@@ -153,7 +169,7 @@ def run_reference(args):
         "note": "reference algorithm (padded per-summand second-barycentric-form contraction) restated in C + OpenMP "
                 "(oracle/smx_oracle.c); the reference's JAX runtime is not installable offline",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -173,6 +189,7 @@ def main():
                     help="multi-GPU partition: points (weak scaling, tables replicated) or output columns (strong scaling: "
                          "every rank evaluates all points for its slice of the value table; for huge d_out)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -189,8 +206,6 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
-        # (NCCL prints its version banner to stdout when NCCL_DEBUG is set: keep stdout to the one JSON line)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = workloads.CONFIGS[args.config]
@@ -377,7 +392,7 @@ def main():
             cpu_layout, cpu_cols = (layout, None) if not compact else oracle_layout(wl)
             v, cores, sample, _ = cpu_reference(wl, cpu_layout, args.cpu_seconds, 1, cpu_cols)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
