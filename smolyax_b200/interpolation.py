@@ -322,40 +322,7 @@ class SmolyakBarycentricInterpolator:
                     quad_tab[rows, slot, : len(qts)] = qts
 
             F = np.zeros((nn,) + tuple(v + 1 for v in tau) + (self._d_out,))
-            pending = []  # (summand, mu, key, point) for batched evaluation
-            for i in range(nn):
-                nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
-                store = f_evals if self._is_nested else f_evals.get(nu, {})
-                s_i = sorted_dims[i]
-                by_dim = np.argsort(s_i)
-                x = zero.copy()
-                F_i = F[i]
-                for mu in it.product(*[range(int(v) + 1) for v in sorted_degs[i]]):
-                    key = tuple((int(s_i[j]), mu[j]) for j in by_dim if mu[j] > 0)
-                    if key not in store:
-                        x[s_i] = [node_tab[i, j, mu[j]] for j in range(n)]
-                        if self._batched_f:
-                            store[key] = None
-                            pending.append((store, key, x.copy()))
-                        else:
-                            store[key] = f(x)
-                        self._n_f_evals_new += 1
-                    if not self._batched_f:
-                        F_i[mu] = store[key]
-                if not self._is_nested:
-                    f_evals[nu] = store
-            if self._batched_f:
-                if pending:
-                    vals = np.asarray(f(np.stack([p[2] for p in pending])), dtype=float).reshape(len(pending), -1)
-                    for (store, key, _), v in zip(pending, vals):
-                        store[key] = v if self._d_out > 1 else (v[0] if v.size == 1 else v)
-                for i in range(nn):
-                    nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
-                    store = f_evals if self._is_nested else f_evals[nu]
-                    s_i = sorted_dims[i]
-                    by_dim = np.argsort(s_i)
-                    for mu in it.product(*[range(int(v) + 1) for v in sorted_degs[i]]):
-                        F[i][mu] = store[tuple((int(s_i[j]), mu[j]) for j in by_dim if mu[j] > 0)]
+            self._fill_values(F, f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab)
 
             layout[f"F_{n}"] = np.ascontiguousarray(np.moveaxis(F, -1, 1))
             layout[f"nodes_{n}"] = node_tab
@@ -366,6 +333,79 @@ class SmolyakBarycentricInterpolator:
             layout[f"quad_{n}"] = quad_tab
 
         return layout, f_evals
+
+    def _fill_values(self, F, f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab):
+        """Function values of one group into ``F (nn, tau_1+1, .., tau_n+1, d_out)``: the reference's walk
+        (interpolation.py:208-228: summands in order, grid points ``mu`` in C order over the sorted slots, ``f`` called at
+        the first occurrence of a node, ``f_evals`` keyed by the ``(dim, mu)`` pairs with ``mu > 0`` in ascending
+        dimension) with the grid enumerated, de-duplicated and scattered by NumPy; Python touches only the nodes that
+        are new to the walk (nested rules: ``n_f_evals`` of them instead of every grid point)."""
+        nn, n = sorted_dims.shape
+        d_out = self._d_out
+        m = sorted_degs + 1
+        stride = np.ones_like(m)
+        for j in range(n - 2, -1, -1):
+            stride[:, j] = stride[:, j + 1] * m[:, j + 1]
+        count = stride[:, 0] * m[:, 0]
+        start = np.concatenate(([0], np.cumsum(count)))
+        total = int(start[-1])
+        si = np.repeat(np.arange(nn), count)
+        local = np.arange(total) - start[si]
+        mu = (local[:, None] // stride[si]) % m[si]  # (total, n): grid index per sorted slot
+        f_stride = np.ones(n, dtype=np.int64)
+        for j in range(n - 2, -1, -1):
+            f_stride[j] = f_stride[j + 1] * F.shape[j + 2]
+        pos = si * int(np.prod(F.shape[1:-1])) + mu @ f_stride
+        sentinel = np.iinfo(np.int64).max
+        rows = np.sort(np.where(mu > 0, sorted_dims[si] * _CODE + mu, sentinel), axis=1)  # key pairs by ascending dim
+
+        if self._is_nested:
+            _, first, inverse = np.unique(rows, axis=0, return_index=True, return_inverse=True)
+            walk = np.argsort(first, kind="stable")  # unique nodes in the order the walk meets them
+            rank = np.empty_like(walk)
+            rank[walk] = np.arange(len(walk))
+            rep, inverse = first[walk], rank[inverse.reshape(-1)]
+            stores = None
+        else:
+            rep, inverse = np.arange(total), np.arange(total)
+            stores = []
+            for i in range(nn):
+                nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
+                stores.append(f_evals.setdefault(nu, {}))
+
+        rep_rows = rows[rep]
+        nnz = (rep_rows != sentinel).sum(axis=1)
+        keys = [None] * len(rep)
+        for r in np.unique(nnz).tolist():  # keys of r pairs at a time: the tuples are built by zip, not in Python code
+            where = np.flatnonzero(nnz == r)
+            sub = rep_rows[where, :r]
+            for u, a, b in zip(where.tolist(), (sub // _CODE).tolist(), (sub % _CODE).tolist()):
+                keys[u] = tuple(zip(a, b))
+        rep_si = si[rep].tolist()
+        missing = [u for u, key in enumerate(keys) if key not in (f_evals if stores is None else stores[rep_si[u]])]
+        self._n_f_evals_new += len(missing)
+        chunk = max(1, (1 << 23) // len(zero))  # <= 64 MB of points at a time
+        for c0 in range(0, len(missing), chunk):
+            part = missing[c0:c0 + chunk]
+            g = rep[part]
+            X = np.tile(zero, (len(part), 1))
+            X[np.arange(len(part))[:, None], sorted_dims[si[g]]] = node_tab[si[g][:, None], np.arange(n)[None, :], mu[g]]
+            if self._batched_f:
+                vals = np.asarray(f(X), dtype=float).reshape(len(part), -1)
+                vals = [v if d_out > 1 else (v[0] if v.size == 1 else v) for v in vals]
+            else:
+                vals = [f(x) for x in X]
+            for u, v in zip(part, vals):
+                (f_evals if stores is None else stores[rep_si[u]])[keys[u]] = v
+        found = [(f_evals if stores is None else stores[rep_si[u]])[key] for u, key in enumerate(keys)]
+        try:
+            table = np.asarray(found, dtype=float).reshape(len(keys), -1)
+            table = np.broadcast_to(table, (len(keys), d_out))
+        except ValueError:  # values of mixed shapes (scalars from the caller's f_evals beside arrays)
+            table = np.empty((len(keys), d_out))
+            for u, v in enumerate(found):
+                table[u] = np.asarray(v, dtype=float).reshape(-1)
+        F.reshape(-1, d_out)[pos] = table[inverse]
 
     # ------------------------------------------------------------------ helpers
     def reference_layout(self) -> dict:
