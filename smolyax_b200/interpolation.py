@@ -188,86 +188,82 @@ class SmolyakBarycentricInterpolator:
         offset = np.zeros(self._d_out)
 
         pool_at, pool_nodes, pool_quad, pool_len = {}, [], [], 0  # (generator, degree) -> offset into the pools
-        row_of, row_src, new_points = {}, [], []  # evaluation -> row of `values`; its value or None (pending)
-        n_active, slot_dims, slot_degs, slot_nodes, zetas, val_off, val_index = [], [], [], [], [], [0], []
+        row_of, value_blocks, n_rows = {}, [], 0  # evaluation -> row of `values` (nested rules share rows)
+        n_active, slot_dims, slot_degs, slot_nodes, zetas, counts, val_index = [], [], [], [], [], [], []
 
         # summands in the order of the reference layout (groups by number of active dimensions in order of first
         # appearance, the reference's walk inside a group): both create entries then add up the same numbers in the same
         # order and the two kinds of handle agree bit for bit
-        groups = sorted(set(lengths.tolist()), key=lambda v: np.flatnonzero(lengths == v)[0])
-        for s in (int(i) for n_grp in groups for i in np.flatnonzero(lengths == n_grp)):
-            n = int(lengths[s])
-            dims_in = dims_all[offsets[s]:offsets[s + 1]].astype(np.int64)
-            degs_in = degs_all[offsets[s]:offsets[s + 1]].astype(np.int64)
-            nu = tuple(zip(dims_in.tolist(), degs_in.tolist()))
-            store = f_evals if self._is_nested else f_evals.setdefault(nu, {})
+        for n in sorted(set(lengths.tolist()), key=lambda v: np.flatnonzero(lengths == v)[0]):
+            sel = np.flatnonzero(lengths == n)
             if n == 0:
+                store = f_evals if self._is_nested else f_evals.setdefault((), {})
                 if () not in store:
                     store[()] = f(zero.copy())
                     self._n_f_evals_new += 1
-                offset = np.asarray(int(zetas_all[s]) * np.asarray(store[()], dtype=float), dtype=float) * np.ones(self._d_out)
+                offset = np.asarray(int(zetas_all[sel[0]]) * np.asarray(store[()], dtype=float), dtype=float) * np.ones(self._d_out)
                 continue
-            order = np.argsort(-degs_in, kind="stable")  # interpolation.py:175; any order is valid for the compact form
-            sd, sg = dims_in[order], degs_in[order]
-            pts = []
-            for dim, deg in zip(sd.tolist(), sg.tolist()):
-                key = (id(gen[dim]), deg)
-                if key not in pool_at:
-                    p = np.asarray(gen[dim](deg), dtype=float)
-                    q = np.zeros(deg + 1)
-                    qw = np.asarray(gen[dim].get_quadrature_weights(deg), dtype=float)
-                    q[: len(qw)] = qw
-                    pool_at[key] = (pool_len, p)
-                    pool_nodes.append(p)
-                    pool_quad.append(q)
-                    pool_len += deg + 1
-                slot_nodes.append(pool_at[key][0])
-                pts.append(pool_at[key][1])
-            n_active.append(n)
-            slot_dims.extend(sd.tolist())
-            slot_degs.extend(sg.tolist())
-            zetas.append(int(zetas_all[s]))
-            by_dim = np.argsort(sd)
-            tag = None if self._is_nested else nu
-            for mu in it.product(*[range(int(v) + 1) for v in sg]):
-                key = tuple((int(sd[j]), mu[j]) for j in by_dim if mu[j] > 0)
-                row = row_of.get((tag, key))
-                if row is None:
-                    row = len(row_src)
-                    row_of[(tag, key)] = row
-                    if key in store:
-                        row_src.append(store[key])
-                    else:
-                        x = zero.copy()
-                        x[sd] = [pts[j][mu[j]] for j in range(n)]
-                        self._n_f_evals_new += 1
-                        if self._batched_f:
-                            row_src.append(None)
-                            new_points.append((row, store, key, x))
-                        else:
-                            store[key] = f(x)
-                            row_src.append(store[key])
-                val_index.append(row)
-            val_off.append(len(val_index))
+            nn = len(sel)
+            gather = offsets[sel][:, None] + np.arange(n)[None, :]
+            dims_in, degs_in = dims_all[gather].astype(np.int64), degs_all[gather].astype(np.int64)
+            order = np.argsort(-degs_in, axis=1, kind="stable")  # interpolation.py:175; any order is valid for the compact form
+            sd, sg = np.take_along_axis(dims_in, order, axis=1), np.take_along_axis(degs_in, order, axis=1)
+            node_tab = np.zeros((nn, n, int(sg.max()) + 1))
+            node_off = np.empty((nn, n), dtype=np.int64)
+            for slot in range(n):
+                codes = sd[:, slot] * _CODE + sg[:, slot]
+                uniq, first = np.unique(codes, return_index=True)
+                for code in uniq[np.argsort(first, kind="stable")].tolist():  # pools grow in the order of the walk
+                    dim, deg = code // _CODE, code % _CODE
+                    key = (id(gen[dim]), deg)
+                    if key not in pool_at:
+                        p = np.asarray(gen[dim](deg), dtype=float)
+                        q = np.zeros(deg + 1)
+                        qw = np.asarray(gen[dim].get_quadrature_weights(deg), dtype=float)
+                        q[: len(qw)] = qw
+                        pool_at[key] = (pool_len, p)
+                        pool_nodes.append(p)
+                        pool_quad.append(q)
+                        pool_len += deg + 1
+                    rows = np.flatnonzero(codes == code)
+                    node_off[rows, slot] = pool_at[key][0]
+                    node_tab[rows, slot, : deg + 1] = pool_at[key][1]
+            n_active.extend([n] * nn)
+            slot_dims.append(sd.reshape(-1))
+            slot_degs.append(sg.reshape(-1))
+            slot_nodes.append(node_off.reshape(-1))
+            zetas.append(zetas_all[sel].astype(np.int64))
+            counts.append(np.prod(sg + 1, axis=1))
 
-        values = np.empty((len(row_src), self._d_out))
-        if new_points:
-            vals = np.asarray(f(np.stack([p[3] for p in new_points])), dtype=float).reshape(len(new_points), -1)
-            for (row, store, key, _), v in zip(new_points, vals):
-                store[key] = v if self._d_out > 1 else (v[0] if v.size == 1 else v)
-                values[row] = v
-        for row, v in enumerate(row_src):
-            if v is not None:
-                values[row] = v
+            si, mu, keys, owner, inverse = self._walk_group(f, f_evals, zero, dims_in, degs_in, sd, sg, node_tab)
+            if self._is_nested:
+                row = np.empty(len(keys), dtype=np.int64)
+                fresh = []
+                for u, key in enumerate(keys):
+                    r = row_of.get(key)
+                    if r is None:
+                        r = row_of[key] = n_rows + len(fresh)
+                        fresh.append(f_evals[key])
+                    row[u] = r
+            else:
+                row = n_rows + np.arange(len(keys))
+                fresh = [store[key] for store, key in zip(owner, keys)]
+            if fresh:
+                value_blocks.append(self._value_rows(fresh))
+                n_rows += len(fresh)
+            val_index.append(row[inverse])
+
+        values = np.concatenate(value_blocks) if value_blocks else np.empty((0, self._d_out))
+        cat = lambda parts: np.concatenate(parts).astype(np.int64) if parts else np.zeros(0, dtype=np.int64)
+        slot_dims, slot_degs, slot_nodes, zetas, val_index = (cat(v) for v in (slot_dims, slot_degs, slot_nodes, zetas, val_index))
+        val_off = np.concatenate([[0], np.cumsum(cat(counts))]).astype(np.int64)
         layout = {
             "compact": True, "offset": offset, "n_active": np.asarray(n_active, dtype=np.int32),
             "slot_off": np.concatenate([[0], np.cumsum(n_active, dtype=np.int64)]).astype(np.int64),
-            "dims": np.asarray(slot_dims, dtype=np.int64), "degs": np.asarray(slot_degs, dtype=np.int64),
-            "node_off": np.asarray(slot_nodes, dtype=np.int64),
+            "dims": slot_dims, "degs": slot_degs, "node_off": slot_nodes,
             "node_pool": np.concatenate(pool_nodes) if pool_nodes else np.zeros(1),
             "quad_pool": np.concatenate(pool_quad) if pool_quad else np.zeros(1),
-            "zetas": np.asarray(zetas, dtype=np.int64), "val_off": np.asarray(val_off, dtype=np.int64),
-            "val_index": np.asarray(val_index, dtype=np.int64), "values": values,
+            "zetas": zetas, "val_off": val_off, "val_index": val_index, "values": np.ascontiguousarray(values),
         }
         return layout, f_evals
 
@@ -334,12 +330,15 @@ class SmolyakBarycentricInterpolator:
 
         return layout, f_evals
 
-    def _fill_values(self, F, f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab):
-        """Function values of one group into ``F (nn, tau_1+1, .., tau_n+1, d_out)``: the reference's walk
-        (interpolation.py:208-228: summands in order, grid points ``mu`` in C order over the sorted slots, ``f`` called at
-        the first occurrence of a node, ``f_evals`` keyed by the ``(dim, mu)`` pairs with ``mu > 0`` in ascending
-        dimension) with the grid enumerated, de-duplicated and scattered by NumPy; Python touches only the nodes that
-        are new to the walk (nested rules: ``n_f_evals`` of them instead of every grid point)."""
+    def _walk_group(self, f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab):
+        """The reference's walk over the grids of one group (interpolation.py:208-228: summands in order, grid points
+        ``mu`` in C order over the sorted slots, ``f`` called at the first occurrence of a node, ``f_evals`` keyed by
+        the ``(dim, mu)`` pairs with ``mu > 0`` in ascending dimension), with the grids enumerated and de-duplicated by
+        NumPy: Python touches only the distinct nodes (nested rules: ``n_f_evals`` of them instead of every grid point).
+
+        Returns ``(si, mu, keys, owner, inverse)``: summand and grid index of every grid point in walk order, the keys
+        of the distinct nodes in the order the walk meets them, the dictionary holding each of them, and the distinct
+        node of every grid point."""
         nn, n = sorted_dims.shape
         d_out = self._d_out
         m = sorted_degs + 1
@@ -352,26 +351,23 @@ class SmolyakBarycentricInterpolator:
         si = np.repeat(np.arange(nn), count)
         local = np.arange(total) - start[si]
         mu = (local[:, None] // stride[si]) % m[si]  # (total, n): grid index per sorted slot
-        f_stride = np.ones(n, dtype=np.int64)
-        for j in range(n - 2, -1, -1):
-            f_stride[j] = f_stride[j + 1] * F.shape[j + 2]
-        pos = si * int(np.prod(F.shape[1:-1])) + mu @ f_stride
         sentinel = np.iinfo(np.int64).max
         rows = np.sort(np.where(mu > 0, sorted_dims[si] * _CODE + mu, sentinel), axis=1)  # key pairs by ascending dim
 
         if self._is_nested:
             _, first, inverse = np.unique(rows, axis=0, return_index=True, return_inverse=True)
-            walk = np.argsort(first, kind="stable")  # unique nodes in the order the walk meets them
+            walk = np.argsort(first, kind="stable")  # distinct nodes in the order the walk meets them
             rank = np.empty_like(walk)
             rank[walk] = np.arange(len(walk))
             rep, inverse = first[walk], rank[inverse.reshape(-1)]
-            stores = None
+            owner = [f_evals] * len(rep)
         else:
             rep, inverse = np.arange(total), np.arange(total)
             stores = []
             for i in range(nn):
                 nu = tuple(zip(dims_in[i].tolist(), degs_in[i].tolist()))
                 stores.append(f_evals.setdefault(nu, {}))
+            owner = [stores[i] for i in si.tolist()]
 
         rep_rows = rows[rep]
         nnz = (rep_rows != sentinel).sum(axis=1)
@@ -381,8 +377,7 @@ class SmolyakBarycentricInterpolator:
             sub = rep_rows[where, :r]
             for u, a, b in zip(where.tolist(), (sub // _CODE).tolist(), (sub % _CODE).tolist()):
                 keys[u] = tuple(zip(a, b))
-        rep_si = si[rep].tolist()
-        missing = [u for u, key in enumerate(keys) if key not in (f_evals if stores is None else stores[rep_si[u]])]
+        missing = [u for u, key in enumerate(keys) if key not in owner[u]]
         self._n_f_evals_new += len(missing)
         chunk = max(1, (1 << 23) // len(zero))  # <= 64 MB of points at a time
         for c0 in range(0, len(missing), chunk):
@@ -396,16 +391,30 @@ class SmolyakBarycentricInterpolator:
             else:
                 vals = [f(x) for x in X]
             for u, v in zip(part, vals):
-                (f_evals if stores is None else stores[rep_si[u]])[keys[u]] = v
-        found = [(f_evals if stores is None else stores[rep_si[u]])[key] for u, key in enumerate(keys)]
+                owner[u][keys[u]] = v
+        return si, mu, keys, owner, inverse
+
+    def _value_rows(self, found):
+        """``(len(found), d_out)`` array of the function values in ``found`` (scalars are broadcast)."""
         try:
-            table = np.asarray(found, dtype=float).reshape(len(keys), -1)
-            table = np.broadcast_to(table, (len(keys), d_out))
+            table = np.asarray(found, dtype=float).reshape(len(found), -1)
+            return np.broadcast_to(table, (len(found), self._d_out))
         except ValueError:  # values of mixed shapes (scalars from the caller's f_evals beside arrays)
-            table = np.empty((len(keys), d_out))
+            table = np.empty((len(found), self._d_out))
             for u, v in enumerate(found):
                 table[u] = np.asarray(v, dtype=float).reshape(-1)
-        F.reshape(-1, d_out)[pos] = table[inverse]
+            return table
+
+    def _fill_values(self, F, f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab):
+        """Function values of one group into ``F (nn, tau_1+1, .., tau_n+1, d_out)`` (interpolation.py:203-228)."""
+        n = sorted_dims.shape[1]
+        si, mu, keys, owner, inverse = self._walk_group(f, f_evals, zero, dims_in, degs_in, sorted_dims, sorted_degs, node_tab)
+        f_stride = np.ones(n, dtype=np.int64)
+        for j in range(n - 2, -1, -1):
+            f_stride[j] = f_stride[j + 1] * F.shape[j + 2]
+        pos = si * int(np.prod(F.shape[1:-1])) + mu @ f_stride
+        table = self._value_rows([store[key] for store, key in zip(owner, keys)])
+        F.reshape(-1, self._d_out)[pos] = table[inverse]
 
     # ------------------------------------------------------------------ helpers
     def reference_layout(self) -> dict:

@@ -132,3 +132,46 @@ def test_vectorised_fill_keeps_the_order_of_the_reference_walk(rule, batched):
         layout2, _ = again._assemble(g1, mixed)
         assert again.n_f_evals_new == 0
         assert all(np.array_equal(layout1[key], layout2[key]) for key in layout1)
+
+
+@pytest.mark.parametrize("rule, batched", [("leja", False), ("leja", True), ("gh", False), ("gh", True)])
+def test_compact_assembly_walks_like_the_padded_one(rule, batched):
+    """Same calls of ``f`` in the same order, same ``f_evals``, and ``values[val_index]`` holds exactly the entries of
+    the padded tensors ``F_n`` at the grid points of each summand (C order over the sorted slots)."""
+    d_in, d_out, t = 6, 2, 6.0
+    k = workloads.anisotropy(d_in)
+    gen = nodes.Leja(dim=d_in) if rule == "leja" else nodes.GaussHermite(dim=d_in)
+    fam = workloads.TargetFamily(d_in, d_out)
+    out = {}
+    for mode in ("reference", "compact"):
+        calls = []
+
+        def f(x):
+            calls.extend(np.atleast_2d(np.asarray(x)).copy())
+            return fam(x)
+
+        ip = SmolyakBarycentricInterpolator(node_gen=gen, k=k, t=t, d_out=d_out, batched_f=batched, layout=mode)
+        layout, evals = (ip._assemble if mode == "reference" else ip._assemble_compact)(f, {})
+        out[mode] = (layout, evals, np.array(calls), ip.n_f_evals_new)
+    (ref, ev_r, calls_r, new_r), (cmp_, ev_c, calls_c, new_c) = out["reference"], out["compact"]
+    assert new_r == new_c and np.array_equal(calls_r, calls_c)
+    assert list(ev_r) == list(ev_c)
+    if rule != "leja":
+        assert all(list(ev_r[nu]) == list(ev_c[nu]) for nu in ev_r)
+    assert np.array_equal(ref["offset"], cmp_["offset"])
+    s = 0
+    for n in [int(key[6:]) for key in ref if key.startswith("zetas_")]:
+        F, degs, dims = ref[f"F_{n}"], ref[f"degs_{n}"], ref[f"dims_{n}"]
+        for i in range(len(degs)):
+            lo, hi = cmp_["slot_off"][s], cmp_["slot_off"][s + 1]
+            assert np.array_equal(cmp_["dims"][lo:hi], dims[i]) and np.array_equal(cmp_["degs"][lo:hi], degs[i])
+            assert cmp_["zetas"][s] == ref[f"zetas_{n}"][i]
+            block = F[i][(slice(None),) + tuple(slice(0, int(v) + 1) for v in degs[i])].reshape(d_out, -1).T
+            rows = cmp_["val_index"][cmp_["val_off"][s]:cmp_["val_off"][s + 1]]
+            assert np.array_equal(cmp_["values"][rows], block)
+            for j in range(n):
+                o = cmp_["node_off"][lo + j]
+                assert np.array_equal(cmp_["node_pool"][o:o + degs[i][j] + 1], ref[f"nodes_{n}"][i, j, :degs[i][j] + 1])
+                assert np.array_equal(cmp_["quad_pool"][o:o + degs[i][j] + 1], ref[f"quad_{n}"][i, j, :degs[i][j] + 1])
+            s += 1
+    assert s == len(cmp_["zetas"]) and cmp_["values"].shape[0] == (new_c if rule == "leja" else new_c - 1)
