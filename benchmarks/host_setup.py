@@ -46,6 +46,12 @@ def ours(wl, reps):
         out, rows["set_f tables" + (" (batched_f)" if batched else "")] = best(assemble, max(1, reps - 1))
         if not batched:  # (a batched f sums in another order: its values differ from per-point calls in the last bit)
             layout = out
+
+        def assemble_compact():
+            ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=k, t=t, d_out=wl.d_out, batched_f=batched,
+                                                layout="compact")
+            return ip._assemble_compact(f, {})[0]
+        _, rows["set_f tables, compact layout" + (" (batched_f)" if batched else "")] = best(assemble_compact, max(1, reps - 1))
     return t, len(lam), nz, layout, rows
 
 
@@ -91,7 +97,7 @@ def main():
             print(f"  value tensors identical to the reference's: {same}")
         print(f"  {'step':38s} {'this package':>14s} {'reference':>12s} {'ratio':>8s}")
         for key, v in rows.items():
-            r = ref_rows.get(key.replace(" (batched_f)", ""))
+            r = ref_rows.get(key.replace(" (batched_f)", "").replace(", compact layout", ""))
             print(f"  {key:38s} {v:14.4f} " + (f"{r:12.4f} {r / v:8.1f}" if r is not None else f"{'-':>12s} {'-':>8s}"))
 
 

@@ -383,7 +383,7 @@ class SmolyakBarycentricInterpolator:
         for c0 in range(0, len(missing), chunk):
             part = missing[c0:c0 + chunk]
             g = rep[part]
-            X = np.tile(zero, (len(part), 1))
+            X = np.tile(zero, (len(part), 1)) if zero.any() else np.zeros((len(part), len(zero)))
             X[np.arange(len(part))[:, None], sorted_dims[si[g]]] = node_tab[si[g][:, None], np.arange(n)[None, :], mu[g]]
             if self._batched_f:
                 vals = np.asarray(f(X), dtype=float).reshape(len(part), -1)
