@@ -16,7 +16,6 @@ handful of CUDA kernel launches instead of a Python loop of XLA dispatches.  The
 from __future__ import annotations
 
 import ctypes
-import itertools as it
 from typing import Callable, Sequence
 
 import numpy as np
@@ -33,6 +32,23 @@ def _host_weights(pts: np.ndarray) -> np.ndarray:
     diffs = pts[:, None] - pts
     diffs = np.where(diffs == 0, 1, diffs)
     return np.prod(1 / diffs, axis=0)
+
+
+def write_layout(layout: dict, path, *, d_in: int, d_out: int, k, t: float) -> None:
+    """``layout`` (reference or compact form) and the identity of its index set as one uncompressed ``.npz``."""
+    arrays = {f"layout/{key}": np.asarray(val) for key, val in layout.items()}
+    np.savez(path, **arrays, **{"meta/d_in": np.int64(d_in), "meta/d_out": np.int64(d_out),
+                                "meta/k": np.asarray(k, dtype=float), "meta/t": np.float64(t)})
+
+
+def read_layout(path):
+    """Inverse of :func:`write_layout`: ``(layout, meta)`` with the arrays bit for bit as written."""
+    with np.load(path) as data:
+        layout = {key[len("layout/"):]: data[key] for key in data.files if key.startswith("layout/")}
+        meta = {"d_in": int(data["meta/d_in"]), "d_out": int(data["meta/d_out"]), "k": data["meta/k"], "t": float(data["meta/t"])}
+    if "compact" in layout:
+        layout["compact"] = bool(layout["compact"])
+    return layout, meta
 
 
 class SmolyakBarycentricInterpolator:
@@ -176,6 +192,23 @@ class SmolyakBarycentricInterpolator:
             else:
                 flags |= _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
                 self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
+
+    def save_layout(self, path) -> None:
+        """Write the tables ``set_f`` assembled to ``path`` (``.npz``), so that another process or a later run can build
+        the device tables with :meth:`load_layout` without evaluating ``f`` again (the reference keeps no such cache:
+        every run of benchmarking/benchmark.py:126-128 re-evaluates the target at all nodes)."""
+        assert self._layout is not None, "The operator has not yet been set up for a target function via `set_f`."
+        write_layout(self._layout, path, d_in=self._d_in, d_out=self._d_out, k=self._k, t=self._t)
+
+    def load_layout(self, path) -> None:
+        """Build the device tables from a file written by :meth:`save_layout`; asserts that the file belongs to this
+        index set (``k``, ``t``) and these dimensions."""
+        layout, meta = read_layout(path)
+        assert meta["d_in"] == self._d_in and meta["d_out"] == self._d_out, \
+            f"{path}: tables are for d_in={meta['d_in']}, d_out={meta['d_out']}"
+        assert meta["t"] == float(self._t) and np.array_equal(meta["k"], np.asarray(self._k, dtype=float)), \
+            f"{path}: tables belong to another index set"
+        self.set_layout(layout)
 
     def _assemble_compact(self, f: Callable, f_evals: dict):
         """Host half of ``set_f`` without the reference's padding: summands in the order of the reference's walk, one

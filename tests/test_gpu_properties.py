@@ -324,3 +324,22 @@ def test_out_buffer_of_each_input_kind():
             ip(x, out=bad)
     with pytest.raises(AssertionError):
         ip(xt, out=out_pin)
+
+
+@pytest.mark.parametrize("mode", ["reference", "compact"])
+def test_tables_from_a_file_give_the_same_bits(tmp_path, mode):
+    """``save_layout`` / ``load_layout``: a handle built from the stored tables (no call of ``f``) evaluates and integrates
+    to the same bits as the handle ``set_f`` built, and differentiates to the same numbers."""
+    from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
+
+    w = workloads.Workload("file", "leja", 15, 2, 400, 0)
+    ip = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=2, f=w.target(), layout=mode)
+    ip.save_layout(tmp_path / "tables.npz")
+    again = SmolyakBarycentricInterpolator(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=2)
+    again.load_layout(tmp_path / "tables.npz")
+    x = w.points(777, seed=5)
+    assert np.array_equal(ip(x), again(x))
+    J, J2 = ip.gradient(x[:50]), again.gradient(x[:50])  # (partial derivatives of split blocks meet in atomics: last bits)
+    assert np.array_equal(np.isnan(J), np.isnan(J2))
+    assert np.max(np.abs(np.nan_to_num(J) - np.nan_to_num(J2))) <= 1e-13 * max(1.0, float(np.nanmax(np.abs(J))))
+    assert np.array_equal(ip.integral(), again.integral())

@@ -175,3 +175,23 @@ def test_compact_assembly_walks_like_the_padded_one(rule, batched):
                 assert np.array_equal(cmp_["quad_pool"][o:o + degs[i][j] + 1], ref[f"quad_{n}"][i, j, :degs[i][j] + 1])
             s += 1
     assert s == len(cmp_["zetas"]) and cmp_["values"].shape[0] == (new_c if rule == "leja" else new_c - 1)
+
+
+@pytest.mark.parametrize("mode", ["reference", "compact"])
+def test_layout_file_round_trip(tmp_path, mode):
+    from smolyax_b200.interpolation import read_layout, write_layout
+
+    d_in, d_out, t = 5, 3, 5.0
+    k = workloads.anisotropy(d_in)
+    ip = SmolyakBarycentricInterpolator(node_gen=nodes.Leja(dim=d_in), k=k, t=t, d_out=d_out, layout=mode)
+    layout, _ = (ip._assemble if mode == "reference" else ip._assemble_compact)(workloads.TargetFamily(d_in, d_out), {})
+    path = tmp_path / "tables.npz"
+    write_layout(layout, path, d_in=d_in, d_out=d_out, k=k, t=t)
+    back, meta = read_layout(path)
+    assert list(back) == list(layout) and bool(back.get("compact")) == (mode == "compact")
+    for key, val in layout.items():
+        assert np.array_equal(np.asarray(val), back[key]) and np.asarray(val).dtype == np.asarray(back[key]).dtype, key
+    assert meta["d_in"] == d_in and meta["d_out"] == d_out and meta["t"] == t and np.array_equal(meta["k"], k)
+    other = SmolyakBarycentricInterpolator(node_gen=nodes.Leja(dim=d_in), k=k, t=t + 0.5, d_out=d_out)
+    with pytest.raises(AssertionError, match="another index set"):
+        other.load_layout(path)
