@@ -19,5 +19,5 @@ def pytest_collection_modifyitems(config, items):
     have_ref = Path("/root/reference/src/smolyax").exists()
     skip_ref = pytest.mark.skip(reason="/root/reference is not present on this machine")
     for item in items:
-        if "reference" in item.keywords and not have_ref:
+        if item.get_closest_marker("reference") is not None and not have_ref:
             item.add_marker(skip_ref)
