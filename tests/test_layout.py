@@ -195,3 +195,49 @@ def test_layout_file_round_trip(tmp_path, mode):
     other = SmolyakBarycentricInterpolator(node_gen=nodes.Leja(dim=d_in), k=k, t=t + 0.5, d_out=d_out)
     with pytest.raises(AssertionError, match="another index set"):
         other.load_layout(path)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("rule", ["leja", "gh"])
+@pytest.mark.parametrize("mode, batched", [("reference", False), ("reference", True), ("compact", False), ("compact", True)])
+def test_set_f_calls_f_like_the_unmodified_reference(rule, mode, batched):
+    """The reference itself (on the NumPy `jax` stand-in, build container only) and this package call ``f`` at the same
+    points in the same order and return the same ``f_evals`` (keys, order, values), also when a dictionary is reused."""
+    import sys
+    from pathlib import Path
+
+    sys.path[:0] = [str(Path(__file__).resolve().parent.parent / "oracle" / "jax_stub"), "/root/reference/src"]
+    from smolyax import nodes as rnodes
+    from smolyax.interpolation import SmolyakBarycentricInterpolator as Reference
+
+    d_in, d_out = 6, 2
+    k = workloads.anisotropy(d_in)
+    fam = workloads.TargetFamily(d_in, d_out)
+
+    def run(cls, gen, t, evals, **kw):
+        calls = []
+
+        def f(x):
+            calls.extend(np.atleast_2d(np.array(x, dtype=float)))
+            return fam(x)
+
+        ip = cls(node_gen=gen, k=k, t=t, d_out=d_out, **kw)
+        if cls is Reference:
+            evals = ip.set_f(f=f, f_evals=evals)
+        else:
+            evals = (ip._assemble if mode == "reference" else ip._assemble_compact)(f, evals)[1]
+        return np.array(calls), evals, ip.n_f_evals_new
+
+    gen_r = rnodes.Leja(dim=d_in) if rule == "leja" else rnodes.GaussHermite(dim=d_in)
+    gen = nodes.Leja(dim=d_in) if rule == "leja" else nodes.GaussHermite(dim=d_in)
+    ev_r, ev = {}, {}
+    for t in (4.0, 5.5):  # the second pass reuses the dictionary of the first
+        calls_r, ev_r, new_r = run(Reference, gen_r, t, ev_r)
+        calls, ev, new = run(SmolyakBarycentricInterpolator, gen, t, ev, batched_f=batched, layout=mode)
+        assert new == new_r and calls.shape == calls_r.shape and np.array_equal(calls, calls_r)
+        assert list(ev) == list(ev_r)
+        same = np.array_equal if not batched else (lambda a, b: np.allclose(a, b, rtol=1e-15, atol=0))  # (f's own rounding)
+        if rule == "leja":
+            assert all(same(ev[key], ev_r[key]) for key in ev)
+        else:
+            assert all(list(ev[nu]) == list(ev_r[nu]) and all(same(ev[nu][key], ev_r[nu][key]) for key in ev[nu]) for nu in ev)
