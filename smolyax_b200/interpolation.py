@@ -268,7 +268,7 @@ class SmolyakBarycentricInterpolator:
             zetas.append(zetas_all[sel].astype(np.int64))
             counts.append(np.prod(sg + 1, axis=1))
 
-            si, mu, keys, owner, inverse = self._walk_group(f, f_evals, zero, dims_in, degs_in, sd, sg, node_tab)
+            _, _, keys, owner, inverse = self._walk_group(f, f_evals, zero, dims_in, degs_in, sd, sg, node_tab)
             if self._is_nested:
                 row = np.empty(len(keys), dtype=np.int64)
                 fresh = []
