@@ -127,6 +127,9 @@ int smx_integral(smx_interp* h, double* q, void* stream);
  * out are pipelined over chunks of `chunk_points` rows (0 = default) on internal streams; returns when y is
  * complete.  This is the reference's `np.asarray(interp(X))` (benchmarking/benchmark.py:131) in one call. */
 int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, double* y_host, int64_t chunk_points);
+/* Sizes the staging buffers and streams of smx_eval_host for batches of n_points rows ahead of the first call - the
+ * counterpart of the reference's `n_inputs` constructor argument, which triggers a warm-up call (interpolation.py:250-251). */
+int smx_prepare(smx_interp* h, int64_t n_points);
 
 /* ---- stateless seam twins (DEVICE pointers inside the descriptor) ------------------------------------------
  * smx_group_eval      = sum over s of jit(vmap(evaluate_tensor_product_interpolant))   barycentric.py:69-123,
@@ -174,8 +177,9 @@ int smx_get_info(const smx_interp* h, smx_info* info);
 int64_t smx_launch_count(void);
 
 const char* smx_last_error(void); /* thread-local message of the last failing call */
-int smx_version(void);            /* 100 * major + minor */
+int smx_version(void);            /* 100 * major + minor; the binding checks it against the struct layouts it was written for */
 const char* smx_arch(void);       /* "sm_100a" */
+const char* smx_build_info(void); /* build stamp: compiler version, hash of the sources the library was built from, flags */
 
 #ifdef __cplusplus
 }

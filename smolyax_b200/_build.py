@@ -7,9 +7,12 @@ Both are written next to this file so that they travel to the GPU box with the r
 """
 from __future__ import annotations
 
+import hashlib
+import json
 import os
 import shutil
 import subprocess
+import time
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -19,7 +22,7 @@ HOST_LIB = PKG / "libsmolyax_host.so"
 CUDA_LIB = PKG / "libsmolyax_b200.so"
 
 HOST_SOURCES = ["smx_host.cpp", "smx_plan.cpp"]
-CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu", "smx_fast_kernel.cu", "smx_fast_multi.cu", "smx_dense_kernel.cu", "smx_plan.cpp"]
+CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu", "smx_fast_kernel.cu", "smx_fast_pipe.cu", "smx_fast_multi.cu", "smx_dense_kernel.cu", "smx_plan.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -37,14 +40,40 @@ def _run(cmd):
     return proc.stdout + proc.stderr
 
 
+def source_hash(files, extra=()) -> str:
+    """SHA-256 over the given source files (names and contents) and the build flags: what a binary is stamped with."""
+    h = hashlib.sha256()
+    for f in sorted(Path(f) for f in files):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    for e in extra:
+        h.update(str(e).encode())
+    return h.hexdigest()[:16]
+
+
+def _stamp_path(lib: Path) -> Path:
+    return lib.with_suffix(".so.stamp")
+
+
+def read_stamp(lib: Path) -> dict:
+    """Stamp written next to a built library: hash of the sources it was built from, compiler, flags, time."""
+    try:
+        return json.loads(_stamp_path(lib).read_text())
+    except Exception:
+        return {}
+
+
 def build_host(force: bool = False) -> Path:
     srcs = [CSRC / s for s in HOST_SOURCES]
-    if not force and _newer(HOST_LIB, srcs + sorted(CSRC.glob("*.h"))):
+    flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread"]
+    digest = source_hash(srcs + sorted(CSRC.glob("*.h")), flags)
+    if not force and HOST_LIB.exists() and read_stamp(HOST_LIB).get("source_hash") == digest:
         return HOST_LIB
     cxx = os.environ.get("CXX", "g++")
     tmp = HOST_LIB.with_suffix(f".so.tmp{os.getpid()}")
-    _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread", *srcs, "-o", tmp])
+    _run([cxx, *flags, *srcs, "-o", tmp])
     os.replace(tmp, HOST_LIB)
+    _stamp_path(HOST_LIB).write_text(json.dumps({"source_hash": digest, "compiler": cxx, "flags": flags, "built": time.strftime("%Y-%m-%dT%H:%M:%S")}))
     return HOST_LIB
 
 
@@ -53,35 +82,61 @@ def nvcc_path():
     return cand if Path(cand).exists() else None
 
 
+LAST_BUILD = {}  # library name -> "rebuilt" | "reused (source hash matches)", for the build report of __graft_entry__.build()
+
+
+def nvcc_version(nvcc) -> str:
+    try:
+        out = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout
+        return next((ln.strip() for ln in out.splitlines() if "release" in ln), "nvcc ?")
+    except Exception:
+        return "nvcc ?"
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every translation unit for sm_100a (objects in csrc/.build, in parallel) and link the shared library."""
+    """Compile every translation unit for sm_100a (objects in csrc/.build, in parallel) and link the shared library.
+
+    The library carries a stamp (smx_build_info(), and a `.stamp` file beside it): hash of its sources and flags, compiler
+    version.  Without `force` the existing binary is reused only when that hash matches the sources in the tree."""
     from concurrent.futures import ThreadPoolExecutor
 
     srcs = [CSRC / s for s in CUDA_SOURCES]
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "smolyax_b200.h"]
-    if not force and _newer(CUDA_LIB, srcs + headers):
+    tuning = bool(os.environ.get("SMX_TUNING"))
+    flags = [*NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--fmad=true"]
+    if tuning:  # A/B timing builds: the kernels' tuning knobs read the environment (smx_plan.h tune_int)
+        flags += ["-DSMX_TUNING", *os.environ.get("SMX_EXTRA_NVCC_FLAGS", "").split()]
+    digest = source_hash(srcs + headers, flags)
+    stamp = read_stamp(CUDA_LIB)
+    if not force and CUDA_LIB.exists() and stamp.get("source_hash") == digest:
+        LAST_BUILD[CUDA_LIB.name] = "reused (source hash matches)"
         return CUDA_LIB
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libsmolyax_b200.so (sm_100a); there is no CPU fallback")
     objdir = CSRC / ".build"
     objdir.mkdir(exist_ok=True)
-    common = [nvcc, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
-              "--fmad=true", "-I", ROOT / "include", "-I", CSRC]
+    common = [nvcc, *flags, "-I", ROOT / "include", "-I", CSRC]
     if verbose:
         common += ["-Xptxas", "-v"]
+    version = nvcc_version(nvcc)
+    text = f"{version}; sources {digest}; built {time.strftime('%Y-%m-%dT%H:%M:%S')}"
 
     def compile_one(src: Path):
-        obj = objdir / (src.name + ".o")
-        if not force and _newer(obj, [src] + headers):
+        obj = objdir / (src.name + (".tuning.o" if tuning else ".o"))
+        extra = [f'-DSMX_BUILD_STAMP="{text}"'] if src.name == "smx_api.cu" else []
+        if not force and not extra and _newer(obj, [src] + headers):
             return obj, ""
-        return obj, _run([*common, "-c", src, "-o", obj])
+        return obj, _run([*common, *extra, "-c", src, "-o", obj])
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
         results = list(pool.map(compile_one, srcs))
     tmp = CUDA_LIB.with_suffix(f".so.tmp{os.getpid()}")
     _run([nvcc, *NVCC_ARCH, "-shared", *[obj for obj, _ in results], "-o", tmp])
     os.replace(tmp, CUDA_LIB)
+    _stamp_path(CUDA_LIB).write_text(json.dumps({"source_hash": digest, "compiler": version, "flags": flags, "tuning": tuning,
+                                                 "built": time.strftime("%Y-%m-%dT%H:%M:%S")}))
+    LAST_BUILD[CUDA_LIB.name] = "rebuilt"
     if verbose:
         print("".join(out for _, out in results))
     return CUDA_LIB

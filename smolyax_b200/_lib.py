@@ -77,6 +77,7 @@ EXPORTS = {
     "smx_gradient": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "smx_integral": (c_int, [c_void_p, c_void_p, c_void_p]),
     "smx_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64]),
+    "smx_prepare": (c_int, [c_void_p, c_int64]),
     "smx_group_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
     "smx_group_gradient": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
     "smx_group_integral": (c_int, [POINTER(GroupDesc), c_int64, c_void_p, c_int, c_void_p]),
@@ -87,17 +88,26 @@ EXPORTS = {
     "smx_last_error": (c_char_p, []),
     "smx_version": (c_int, []),
     "smx_arch": (c_char_p, []),
+    "smx_build_info": (c_char_p, []),
 }
 
 
+ABI_VERSION = 200  # smx_version() of the library these ctypes struct layouts were written for
+
+
 def _load():
-    path = _build.CUDA_LIB
-    if not path.exists():
-        path = _build.build_cuda()  # raises if nvcc is missing: no CPU fallback
+    # build_cuda() returns at once when the binary's stamp matches the sources in the tree and rebuilds it otherwise; a box
+    # without nvcc (never the case in this image) keeps whatever binary travelled with the tree.  No CPU fallback either way.
+    if _build.nvcc_path() is not None or not _build.CUDA_LIB.exists():
+        path = _build.build_cuda()
+    else:
+        path = _build.CUDA_LIB
     lib = ctypes.CDLL(str(path))
     for name, (restype, argtypes) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
         fn.restype, fn.argtypes = restype, argtypes
+    if lib.smx_version() != ABI_VERSION:
+        raise ImportError(f"{path} reports ABI {lib.smx_version()}, this binding is written for {ABI_VERSION}: stale binary")
     return lib
 
 

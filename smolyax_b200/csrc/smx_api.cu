@@ -31,6 +31,7 @@ struct smx_interp {
     int64_t d_in = 0, d_out = 0;
     smx_info info{};
     bool has_fast = false, has_groups = false, grad_finite = false, compact = false;
+    bool no_groups_by_depth = false;  // reference layout not uploaded: a summand has more active dimensions than the per-summand kernels take
     double* d_integral = nullptr;  // compact handles: the integral, computed at create time
     FastDevice fast;
     std::vector<SeamGroup> groups;
@@ -48,6 +49,20 @@ struct smx_interp {
 };
 
 namespace {
+
+// The entry points that switch the CUDA device (create, destroy, the host pipeline) put the caller's device back on return.
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&saved) != cudaSuccess) {
+            saved = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard() {
+        if (saved >= 0) cudaSetDevice(saved);
+    }
+};
 
 template <class T>
 int upload_array(smx_interp* h, const T* host, size_t count, const T** out) {
@@ -81,6 +96,7 @@ int check_device(int device, int* resolved) {
 
 void release(smx_interp* h) {
     if (!h) return;
+    DeviceGuard guard;
     cudaSetDevice(h->device);
     fast_free(h->fast);
     for (void* p : h->owned) cudaFree(p);
@@ -112,7 +128,7 @@ int ensure_stages(smx_interp* h, int64_t points, int64_t ldx) {
 
 PlanOptions plan_options(uint32_t flags, int64_t d_out, bool sparse_wanted) {
     PlanOptions opt;
-    static const int dense_min = std::getenv("SMX_DENSE_MIN") ? std::atoi(std::getenv("SMX_DENSE_MIN")) : 32;
+    static const int dense_min = tune_int("SMX_DENSE_MIN", 32);
     opt.dense = (flags & SMX_DENSE_PATH) || (!(flags & SMX_NO_DENSE_PATH) && d_out >= dense_min);
     // the block-sparse form stores every coefficient set padded to 16-entry blocks: beyond a few thousand outputs it
     // only costs memory once the dense form exists (it would still serve the gradient)
@@ -162,6 +178,7 @@ int smx_create_compact(int64_t d_in, int64_t d_out, const double* offset, const 
     *out = nullptr;
     if (d_in <= 0 || d_out <= 0) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: d_in and d_out must be positive");
     int dev = 0, rc;
+    DeviceGuard guard;
     if ((rc = check_device(device, &dev))) return rc;
     std::unique_ptr<smx_interp, void (*)(smx_interp*)> h(new smx_interp(), release);
     h->device = dev;
@@ -186,6 +203,8 @@ int smx_create_compact(int64_t d_in, int64_t d_out, const double* offset, const 
     {
         FastPlan plan;
         const std::string err = build_fast_plan_compact(d_in, d_out, offset, cv, plan, plan_options(flags, d_out, true));
+        if (err.rfind("ill-conditioned", 0) == 0)  // (no per-summand kernels behind a compact handle: the caller uses smx_create)
+            return fail(SMX_ERR_UNSUPPORTED, "smx_create_compact: " + err + "; use the reference layout (smx_create), which falls back to the per-summand kernels");
         if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create_compact: " + err);
         if ((rc = adopt_plan(h.get(), plan))) return rc;
     }
@@ -209,6 +228,7 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
     if (desc->d_in <= 0 || desc->d_out <= 0) return fail(SMX_ERR_INVALID_ARG, "smx_create: d_in and d_out must be positive");
     if (desc->n_groups < 0 || (desc->n_groups > 0 && !desc->groups)) return fail(SMX_ERR_INVALID_ARG, "smx_create: bad group list");
     int dev = 0, rc;
+    DeviceGuard guard;
     if ((rc = check_device(device, &dev))) return rc;
 
     std::unique_ptr<smx_interp, void (*)(smx_interp*)> h(new smx_interp(), release);
@@ -242,8 +262,10 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
     if (want_fast) {
         FastPlan plan;
         const std::string err = build_fast_plan(desc->d_in, desc->d_out, desc->offset, views, plan, plan_options(desc->flags, desc->d_out, true));
-        if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create: " + err);
-        rc = adopt_plan(h.get(), plan);
+        const bool ill = err.rfind("ill-conditioned", 0) == 0;  // high-degree non-nested rule: per-summand kernels (reference arithmetic)
+        if (!err.empty() && !ill) return fail(SMX_ERR_INVALID_ARG, "smx_create: " + err);
+        rc = ill ? (int)SMX_ERR_UNSUPPORTED : adopt_plan(h.get(), plan);
+        if (ill) set_error("smx_create: " + err);
         if (rc == SMX_ERR_UNSUPPORTED) {
             fast_free(h->fast);  // fall back to the per-summand kernels; still a CUDA path
             want_groups = true;
@@ -251,11 +273,30 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
             return rc;
         }
     }
+    // Summands with more active dimensions than the per-summand kernels take (8): with a fast path the handle does without
+    // the reference layout on the device - values and gradients come from the fast path, the integral (which does not
+    // depend on x) is computed here in extended precision, as for compact handles.
+    bool deep_groups = false;
+    for (const GroupView& v : views) deep_groups = deep_groups || v.n > kSeamMaxN;
+    if (want_groups && deep_groups) {
+        if (!h->has_fast) return fail(SMX_ERR_UNSUPPORTED, "smx_create: more than 8 active dimensions per summand and no fast path for this layout");
+        want_groups = false;
+        bool quad = !views.empty();
+        for (const GroupView& v : views) quad = quad && v.quad != nullptr;
+        if (quad) {
+            std::vector<double> Q;
+            const std::string err = integrate_groups(desc->d_out, desc->offset, views, Q);
+            if (!err.empty()) return fail(SMX_ERR_INVALID_ARG, "smx_create: " + err);
+            SMX_CUDA(cudaMalloc((void**)&h->d_integral, sizeof(double) * desc->d_out));
+            SMX_CUDA(cudaMemcpy(h->d_integral, Q.data(), sizeof(double) * desc->d_out, cudaMemcpyHostToDevice));
+            h->info.device_bytes += (int64_t)sizeof(double) * desc->d_out;
+        }
+        h->no_groups_by_depth = true;
+    }
     if (want_groups) {
         for (size_t gi = 0; gi < views.size(); ++gi) {
             const smx_group_desc& d = desc->groups[gi];
             const GroupView& v = views[gi];
-            if (d.n > kSeamMaxN) return fail(SMX_ERR_UNSUPPORTED, "smx_create: more than 8 active dimensions per summand");
             smx_group_desc dd = d;
             const size_t slots = (size_t)d.nn * d.n, tw = (size_t)v.tw();
             if ((rc = upload_array(h.get(), d.F, (size_t)d.nn * desc->d_out * v.fsize(), &dd.F))) return rc;
@@ -316,6 +357,8 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
     if (h->has_fast && h->fast.has_sparse && h->fast.grad_ok) return fast_gradient(h->fast, x, N, ldx, J, !h->grad_finite, st);
     if (h->compact)
         return fail(SMX_ERR_UNSUPPORTED, "smx_gradient: the derivative coefficient sets of this handle were not built (d_out too large)");
+    if (h->no_groups_by_depth)
+        return fail(SMX_ERR_UNSUPPORTED, "smx_gradient: no derivative sets on this handle and more than 8 active dimensions per summand");
     if (!h->has_groups && h->info.n_summands > 0)
         return fail(SMX_ERR_INVALID_ARG, "smx_gradient: no derivative sets and no reference layout (SMX_KEEP_GROUPS) on this handle");
     SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * h->d_out * h->d_in, st));
@@ -327,7 +370,7 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
 
 int smx_integral(smx_interp* h, double* q, void* stream) {
     if (!h || !q) return fail(SMX_ERR_INVALID_ARG, "smx_integral: null argument");
-    if (h->compact) {
+    if (h->compact || h->no_groups_by_depth) {
         if (!h->d_integral) return fail(SMX_ERR_INVALID_ARG, "smx_integral: handle was created without quadrature weights");
         SMX_CUDA(cudaMemcpyAsync(q, h->d_integral, sizeof(double) * h->d_out, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
         return SMX_OK;
@@ -346,46 +389,55 @@ int smx_integral(smx_interp* h, double* q, void* stream) {
     return SMX_OK;
 }
 
+static int64_t default_chunk_points(const smx_interp* h);
+
+int smx_prepare(smx_interp* h, int64_t n_points) {
+    if (!h || n_points < 0) return fail(SMX_ERR_INVALID_ARG, "smx_prepare: bad arguments");
+    if (n_points == 0) return SMX_OK;
+    std::lock_guard<std::mutex> lock(h->host_mutex);
+    DeviceGuard guard;
+    SMX_CUDA(cudaSetDevice(h->device));
+    return ensure_stages(h, std::min(default_chunk_points(h), n_points), h->d_in);
+}
+
 int smx_eval_host(smx_interp* h, const double* x_host, int64_t N, int64_t ldx, double* y_host, int64_t chunk_points) {
     if (!h || N < 0) return fail(SMX_ERR_INVALID_ARG, "smx_eval_host: bad arguments");
     if (N == 0) return SMX_OK;
     if (!x_host || !y_host || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_eval_host: null buffer or ldx < d_in");
     std::lock_guard<std::mutex> lock(h->host_mutex);
+    DeviceGuard guard;
     SMX_CUDA(cudaSetDevice(h->device));
-    if (chunk_points <= 0) {
-        // ~32 MiB per stage keeps the copy engines and the SMs busy at the same time (measured 8 .. 1024 MiB: 149 .. 175 ms
-        // per 8 GB at cfg2, i.e. the PCIe link - 54 GB/s - whatever the chunk)
-        static const long long chunk_mb = std::getenv("SMX_HOST_CHUNK_MB") ? std::atoll(std::getenv("SMX_HOST_CHUNK_MB")) : 32;
-        chunk_points = std::max<int64_t>(1024, (chunk_mb << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
-        // whole waves of 32-point tiles (two CTAs per SM; the GEMM-regime kernel runs ceil(d_out / 128 .. 512) CTAs per tile):
-        // a chunk that fills 44 % of the CTA slots takes as long as a full one.  It does not matter while the link is the
-        // bound (cfg2), it does when the kernel is (cfg5, 32 MiB = 4 194 points = 131 of 296 slots: 467 ms per 10^6 points
-        // end to end against 78 ms of kernel time and 150 ms of copies)
-        if (h->has_fast && h->fast.sm_count > 0) {
-            const int64_t per_tile = h->d_out >= 384 ? (h->d_out + 511) / 512 : (h->d_out + 127) / 128;
-            const int64_t wave = std::max<int64_t>(1, ((int64_t)h->fast.sm_count * 2 + per_tile - 1) / per_tile) * 32;
-            chunk_points = (chunk_points + wave - 1) / wave * wave;
-        }
-    }
+    if (chunk_points <= 0) chunk_points = default_chunk_points(h);
     chunk_points = std::min(chunk_points, N);
     int rc;
     if ((rc = ensure_stages(h, chunk_points, ldx))) return rc;
+    // on any failure: wait for the copies already queued (they read and write the caller's buffers) before returning
+    auto drain = [&](int status) {
+        for (int s = 0; s < smx_interp::kStages; ++s)
+            if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
+        return status;
+    };
     int64_t done = 0;
     for (int64_t c = 0; done < N; ++c, done += chunk_points) {
         const int s = (int)(c % smx_interp::kStages);
         const int64_t n = std::min(chunk_points, N - done);
         cudaStream_t st = h->streams[s];
         // stream order protects the stage buffers: the next use of stage s is queued behind this one
+        cudaError_t e;
         if (ldx == h->d_in)  // contiguous rows: one linear copy
-            SMX_CUDA(cudaMemcpyAsync(h->stage_x[s], x_host + done * ldx, sizeof(double) * (size_t)n * h->d_in, cudaMemcpyHostToDevice, st));
+            e = cudaMemcpyAsync(h->stage_x[s], x_host + done * ldx, sizeof(double) * (size_t)n * h->d_in, cudaMemcpyHostToDevice, st);
         else
-            SMX_CUDA(cudaMemcpy2DAsync(h->stage_x[s], sizeof(double) * h->d_in, x_host + done * ldx, sizeof(double) * ldx,
-                                       sizeof(double) * h->d_in, (size_t)n, cudaMemcpyHostToDevice, st));
-        if ((rc = smx_eval(h, h->stage_x[s], n, h->d_in, h->stage_y[s], st))) return rc;
-        SMX_CUDA(cudaMemcpyAsync(y_host + done * h->d_out, h->stage_y[s], sizeof(double) * (size_t)n * h->d_out,
-                                 cudaMemcpyDeviceToHost, st));
+            e = cudaMemcpy2DAsync(h->stage_x[s], sizeof(double) * h->d_in, x_host + done * ldx, sizeof(double) * ldx,
+                                  sizeof(double) * h->d_in, (size_t)n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return drain(cuda_fail(e, "smx_eval_host: copy of x to the device"));
+        if ((rc = smx_eval(h, h->stage_x[s], n, h->d_in, h->stage_y[s], st))) return drain(rc);
+        e = cudaMemcpyAsync(y_host + done * h->d_out, h->stage_y[s], sizeof(double) * (size_t)n * h->d_out, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return drain(cuda_fail(e, "smx_eval_host: copy of y to the host"));
     }
-    for (int s = 0; s < smx_interp::kStages; ++s) SMX_CUDA(cudaStreamSynchronize(h->streams[s]));
+    for (int s = 0; s < smx_interp::kStages; ++s) {
+        const cudaError_t e = cudaStreamSynchronize(h->streams[s]);
+        if (e != cudaSuccess) return drain(cuda_fail(e, "smx_eval_host: cudaStreamSynchronize"));
+    }
     return SMX_OK;
 }
 
@@ -444,7 +496,33 @@ int smx_basis(const double* x, int64_t N, const double* xi, const double* w, int
 
 int64_t smx_launch_count(void) { return g_launches.load(); }
 const char* smx_last_error(void) { return t_error.c_str(); }
-int smx_version(void) { return 1; }
+int smx_version(void) { return 200; }
 const char* smx_arch(void) { return "sm_100a"; }
+#ifndef SMX_BUILD_STAMP
+#define SMX_BUILD_STAMP "unstamped build"
+#endif
+const char* smx_build_info(void) {
+#ifdef SMX_TUNING
+    return SMX_BUILD_STAMP "; SMX_TUNING";
+#else
+    return SMX_BUILD_STAMP;
+#endif
+}
 
 }  // extern "C"
+
+// ~32 MiB per stage keeps the copy engines and the SMs busy at the same time (measured 8 .. 1024 MiB: 149 .. 175 ms per
+// 8 GB at cfg2, i.e. the PCIe link - 54 GB/s - whatever the chunk), rounded up to whole waves of 32-point tiles (two CTAs
+// per SM; the GEMM-regime kernel runs ceil(d_out / 128 .. 512) CTAs per tile): a chunk that fills 44 % of the CTA slots
+// takes as long as a full one.  It does not matter while the link is the bound (cfg2), it does when the kernel is (cfg5,
+// 32 MiB = 4 194 points = 131 of 296 slots: 467 ms per 10^6 points end to end against 78 ms of kernel time).
+static int64_t default_chunk_points(const smx_interp* h) {
+    const long long chunk_mb = tune_int("SMX_HOST_CHUNK_MB", 32);
+    int64_t chunk_points = std::max<int64_t>(1024, (chunk_mb << 20) / (int64_t)(std::max(h->d_in, h->d_out) * sizeof(double)));
+    if (h->has_fast && h->fast.sm_count > 0) {
+        const int64_t per_tile = h->d_out >= 384 ? (h->d_out + 511) / 512 : (h->d_out + 127) / 128;
+        const int64_t wave = std::max<int64_t>(1, ((int64_t)h->fast.sm_count * 2 + per_tile - 1) / per_tile) * 32;
+        chunk_points = (chunk_points + wave - 1) / wave * wave;
+    }
+    return chunk_points;
+}

@@ -388,16 +388,16 @@ bool dense_kernel_fits(int n_tab, int smem_optin) { return dense_smem_bytes(n_ta
 // A-fragment loads per DMMA).  Few outputs: 8 warps x 1 or 2 blocks with a deeper B ring, two CTAs per SM when the value
 // table leaves room (more independent DMMA chains and loads in flight per SM).
 int dense_kernel_launch(const DenseArgs& args, const double* x, double* y, cudaStream_t st) {
-    static const int want_nb = std::getenv("SMX_DENSE_NB") ? std::atoi(std::getenv("SMX_DENSE_NB")) : 0;
-    static const int want_nw = std::getenv("SMX_DENSE_NW") ? std::atoi(std::getenv("SMX_DENSE_NW")) : 0;
-    static const int want_ctas = std::getenv("SMX_DENSE_CTAS") ? std::atoi(std::getenv("SMX_DENSE_CTAS")) : 0;
-    static const int want_skew = std::getenv("SMX_DENSE_SKEW") ? std::atoi(std::getenv("SMX_DENSE_SKEW")) : 1;
+    static const int want_nb = tune_int("SMX_DENSE_NB", 0);
+    static const int want_nw = tune_int("SMX_DENSE_NW", 0);
+    static const int want_ctas = tune_int("SMX_DENSE_CTAS", 0);
+    static const int want_skew = tune_int("SMX_DENSE_SKEW", 1);
     DenseArgs a = args;
     a.skew = want_skew;
     int device = 0, smem_sm = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    static const int want_splitk = std::getenv("SMX_DENSE_SPLITK") ? std::atoi(std::getenv("SMX_DENSE_SPLITK")) : -1;
+    static const int want_splitk = tune_int("SMX_DENSE_SPLITK", -1);
     // up to 40 output blocks (320 columns): column groups of at most 8 blocks (the accumulators of 32 points x 64 columns
     // are 128 registers per thread), K split over the warps of a CTA
     // (measured: 0.76 vs 0.63 of the DMMA rate at 8 blocks; with two or more groups the staged kernel below wins)

@@ -114,15 +114,49 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     std::vector<double> packed;
     std::vector<int32_t> kstep_off;
     pack_coefficients(plan, packed, kstep_off);
-    // Balanced static schedule for the chosen CTA shape: longest-processing-time assignment of the work items to the
-    // warps (cost ~ fixed part + k-steps), then every warp alternates big and small items so that tensor-heavy and
-    // streaming items are always in flight together.  Directory and metadata records are stored in that order.
-    std::vector<int32_t> dir((size_t)plan.n_chunks * 4), meta((size_t)plan.n_chunks * kMetaInts);
-    std::vector<int32_t> fac2(dev.deep ? (size_t)plan.n_chunks * 64 : 0);  // deep records: factors 5..8 of every row slot
+    // One record per (work item, coefficient set): metadata (640 B; every value-table row index pre-multiplied by kTabPitch,
+    // i.e. an offset in doubles) followed by the set's packed coefficients, so that the kernel stages an item with ONE bulk
+    // copy.  rec_off[c] = offset of item c's first record in units of 128 bytes; the records of the other sets follow at a
+    // stride of 5 + 4 * ksteps units (+ 2 for the second factor list of deep records).
+    const size_t nsets = (size_t)plan.n_sets, extra = dev.deep ? 2 : 0;
+    std::vector<int32_t> rec_off((size_t)plan.n_chunks);
+    if (dev.pipe_warps > 0) dev.pipe_warps = pipe_kernel_workers(dev, smem_optin);  // (marker set by fast_kernel_prepare: eligible)
     {
-        const int nw = dev.warps;
-        double ca = 2.0, cb = 1.0, cc = 0.0;  // cost model of an item: fixed + per k-step + extra for streaming x
-        if (const char* env = std::getenv("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf", &ca, &cb, &cc);
+        size_t units = 0;
+        for (int32_t c = 0; c < plan.n_chunks; ++c)
+            units += nsets * (5 + extra + 4 * (size_t)((plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4));
+        if (units >= (size_t)INT32_MAX) return fail(SMX_ERR_UNSUPPORTED, "too many coefficient sets for the block-sparse form");
+        std::vector<double> records(units * 16, 0.0);
+        std::vector<int32_t> meta(kMetaInts), fac2(64);
+        size_t at = 0;
+        for (int32_t c = 0; c < plan.n_chunks; ++c) {
+            const size_t ksteps = (size_t)((plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4), k0 = (size_t)kstep_off[c];
+            std::copy_n(&plan.chunk_meta[(size_t)c * kMetaInts], kMetaInts, meta.begin());
+            for (int i = 0; i < 16; ++i) meta[i] *= kTabPitch, meta[48 + i] *= kTabPitch;
+            for (int i = 96; i < 160; ++i) meta[i] *= kTabPitch;
+            if (dev.deep)
+                for (int i = 0; i < 64; ++i) fac2[i] = plan.chunk_fac2[(size_t)c * 64 + i] * kTabPitch;
+            rec_off[c] = (int32_t)at;
+            for (size_t o = 0; o < nsets; ++o) {
+                std::memcpy(&records[at * 16], meta.data(), kMetaInts * 4);
+                std::memcpy(&records[(at + 5) * 16], &packed[(k0 + o * ksteps) * kKStepDoubles], ksteps * kKStepDoubles * 8);
+                if (dev.deep) std::memcpy(&records[(at + 5 + 4 * ksteps) * 16], fac2.data(), 256);
+                at += 5 + extra + 4 * ksteps;
+            }
+        }
+        std::vector<double>().swap(packed);
+        if ((rc = upload(records, &dev.coef, dev.bytes, 2))) return rc;
+    }
+    // Balanced static schedule for a CTA shape of nw warps: longest-processing-time assignment of the work items to the
+    // warps (cost ~ fixed part + k-steps), then every warp alternates big and small items so that tensor-heavy and
+    // streaming items are always in flight together.  The directory is stored in that order: per item the offset of its
+    // first record, its rows, flags | nf << 8 | record size in 128-byte units << 16 | k-steps << 24, first column of x.
+    auto build_directory = [&](int nw, std::vector<int32_t>& dir, int32_t* warp_off, bool pipe) {
+        dir.assign((size_t)plan.n_chunks * 4, 0);
+        // cost model of an item: fixed + per k-step + extra for streaming x (measured at the headline configuration, ms per
+        // 10^6 points: barrier kernels 2,1,0; pipelined kernel 2,1,0: 1.684, 2,1,1: 1.651, 1,1,1: 1.659, 3,1,1: 1.694, 2,1,2: 1.781)
+        double ca = 2.0, cb = 1.0, cc = pipe ? 1.0 : 0.0;
+        if (const char* env = tune_str("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf", &ca, &cb, &cc);
         auto cost = [&](int32_t c) {
             return ca + cb * (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4) + ((plan.chunk_flags[c] & kChunkHot) ? 0.0 : cc);
         };
@@ -138,55 +172,30 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         }
         size_t pos = 0;
         for (int w = 0; w < nw; ++w) {
-            dev.warp_off[w] = (int32_t)pos;
+            warp_off[w] = (int32_t)pos;
             const std::vector<int32_t>& l = lists[w];  // sorted by cost, descending
             for (size_t lo = 0, hi = l.size(), k = 0; lo < hi; ++k) {
                 const int32_t c = (k & 1) ? l[--hi] : l[lo++];
-                dir[pos * 4 + 0] = kstep_off[c];
+                const int32_t ks = (plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4;
+                dir[pos * 4 + 0] = rec_off[c];
                 dir[pos * 4 + 1] = plan.chunk_dir[(size_t)c * 4 + 1];
-                {   // flags | nf << 8, plus (lean kernel) the record size in 128-byte units << 16 and the k-steps << 24
-                    const int32_t ks = (plan.chunk_dir[(size_t)c * 4 + 1] + 3) / 4;
-                    dir[pos * 4 + 2] = (plan.chunk_dir[(size_t)c * 4 + 2] & 0xffff) | ((5 + 4 * ks + (dev.deep ? 2 : 0)) << 16) | (ks << 24);
-                }
-                if (dev.deep)
-                    for (int i = 0; i < 64; ++i) fac2[pos * 64 + i] = plan.chunk_fac2[(size_t)c * 64 + i] * kTabPitch;
+                dir[pos * 4 + 2] = (plan.chunk_dir[(size_t)c * 4 + 2] & 0xffff) | ((5 + 4 * ks + (dev.deep ? 2 : 0)) << 16) | (ks << 24);
                 dir[pos * 4 + 3] = plan.chunk_dir[(size_t)c * 4 + 3];
-                std::copy_n(&plan.chunk_meta[(size_t)c * kMetaInts], kMetaInts, &meta[pos * kMetaInts]);
-                // table rows -> offsets in doubles (saves the kernel a multiply per table access)
-                for (int i = 0; i < 16; ++i) meta[pos * kMetaInts + i] *= kTabPitch, meta[pos * kMetaInts + 48 + i] *= kTabPitch;
-                for (int i = 96; i < 160; ++i) meta[pos * kMetaInts + i] *= kTabPitch;
                 ++pos;
             }
         }
-        for (int w = nw; w <= kMaxWarps; ++w) dev.warp_off[w] = (int32_t)pos;
+        for (int w = nw; w <= kMaxWarps; ++w) warp_off[w] = (int32_t)pos;
+    };
+    {
+        std::vector<int32_t> dir;
+        build_directory(dev.warps, dir, dev.warp_off, false);
+        if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
+        if (dev.pipe_warps > 0) {  // the pipelined kernel has its own worker count, hence its own item lists
+            build_directory(dev.pipe_warps, dir, dev.pipe_warp_off, true);
+            if ((rc = upload(dir, &dev.pipe_dir, dev.bytes, 4))) return rc;
+        }
     }
     if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
-    // One record per (work item, coefficient set): metadata (640 B) followed by the set's packed coefficients, so that the
-    // kernel stages an item with ONE bulk copy.  dir[0] = offset of the item's first record in units of 128 bytes; the
-    // records of the other sets follow at a stride of 5 + 4 * ksteps units.
-    {
-        std::vector<double> records;
-        const size_t nsets = (size_t)plan.n_sets;
-        size_t units = 0;
-        const size_t extra = dev.deep ? 2 : 0;  // deep records end with the second factor list (256 bytes)
-        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) units += nsets * (5 + extra + 4 * (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4));
-        if (units >= (size_t)INT32_MAX) return fail(SMX_ERR_UNSUPPORTED, "too many coefficient sets for the block-sparse form");
-        records.assign(units * 16, 0.0);
-        size_t at = 0;
-        for (int32_t pos = 0; pos < plan.n_chunks; ++pos) {
-            const size_t ksteps = (size_t)((dir[(size_t)pos * 4 + 1] + 3) / 4), k0 = (size_t)dir[(size_t)pos * 4];
-            dir[(size_t)pos * 4] = (int32_t)at;
-            for (size_t o = 0; o < nsets; ++o) {
-                std::memcpy(&records[at * 16], &meta[(size_t)pos * kMetaInts], kMetaInts * 4);
-                std::memcpy(&records[(at + 5) * 16], &packed[(k0 + o * ksteps) * kKStepDoubles], ksteps * kKStepDoubles * 8);
-                if (dev.deep) std::memcpy(&records[(at + 5 + 4 * ksteps) * 16], &fac2[(size_t)pos * 64], 256);
-                at += 5 + extra + 4 * ksteps;
-            }
-        }
-        std::vector<double>().swap(packed);
-        if ((rc = upload(records, &dev.coef, dev.bytes, 2))) return rc;
-    }
-    if ((rc = upload(dir, &dev.chunk_dir, dev.bytes, 4))) return rc;
     dev.n_sets = plan.n_sets;
     dev.n_gd = (int32_t)plan.grad_dims.size();
     dev.grad_ok = !dev.deep && (dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
@@ -197,7 +206,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
 }
 
 void fast_free(FastDevice& d) {
-    void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.chunk_meta, d.coef, d.c0,
+    void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.pipe_dir, d.chunk_meta, d.coef, d.c0,
                     d.grad_dims, d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef,
                     d.dense_grad_coef, d.dense_grad_c0, d.dense_grad_col};
     for (void* p : ptrs)
@@ -260,6 +269,9 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.hot_dims = d.hot_dims;
     a.n_pairs = d.n_pairs;
     a.flat = d.flat ? 1 : 0;
+    a.ablate = tune_int("SMX_ABL_KERNEL", 0);
+    a.dbg = nullptr;
+    a.nwk = 0;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
     const int rc = fast_kernel_launch(d, a, x, out, st);
     if (scratch) cudaFreeAsync(scratch, st);

@@ -34,6 +34,9 @@ struct FastArgs {
     long long d_in;
     int n_hot, n_hot_rows, n_tab, n_chunks, n_levels, hot_dims, n_pairs;
     int flat;                // 1: the value table holds the hot rows only, product rows are multiplied on the fly
+    int ablate;              // tuning builds only (SMX_TUNING): timing experiments, 0 in the product library
+    int nwk;                 // pipelined kernel: number of worker warps (warp nwk is the service warp)
+    unsigned long long* dbg; // tuning builds only: per-tile time stamps of CTA 0 (service warp and worker 0), else nullptr
     int level_off[kMaxLevels + 2];
     int warp_off[kMaxWarps + 1];  // work items of warp w are [warp_off[w], warp_off[w + 1]) of the (re-ordered) directory
 };
@@ -56,5 +59,8 @@ int fast_kernel_prepare(FastDevice& d);
 bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* warps);
 int multi_kernel_launch(const CUtensorMap& map, const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);
 int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);
+// single output, FLAT plans: warp-specialised persistent kernel without CTA-wide barriers (smx_fast_pipe.cu)
+int pipe_kernel_workers(const FastDevice& d, int smem_optin);  // worker warps that fit (0: the kernel cannot run this plan)
+int pipe_kernel_launch(const CUtensorMap& map, const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);
 
 }  // namespace smx

@@ -77,5 +77,40 @@ __device__ __forceinline__ void dmma_first(double (&c)[2], double a, double b) {
 }
 
 
+// ---- staging of one work item by one lane (lean / pipelined kernels) -------------------------------------------------
+// The shared-memory directory of these kernels holds, per item: the global address of its first record (x, y), then
+// flags | nf << 8 | record size in 128-byte units << 16 | k-steps << 24 (z; bit 7 = last item of its warp), first column (w).
+constexpr int kDirLast = 0x80;
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Item buffer + its mbarrier; the two of a warp sit back to back, so ONE signed stride flips every pointer into them.
+// DEEP (hot parts of five to eight pairs): the record ends with a second factor list, factors 5..8 of every row slot,
+// which lands right behind the item's coefficients (at most at `fac2`).
+template <bool DEEP>
+struct alignas(16) LeanStage {
+    ItemBuffer item;
+    unsigned long long bar, pad;
+};
+template <>
+struct alignas(16) LeanStage<true> {
+    ItemBuffer item;
+    int4 fac2[16];
+    unsigned long long bar, pad;
+};
+template <bool DEEP>
+__host__ __device__ constexpr size_t lean_stage_bytes() { return 2 * sizeof(LeanStage<DEEP>); }  // per warp
+__device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* item, const void* bar, double* xs, const int4 dir, int o, int p0) {
+    const unsigned bytes = ((unsigned)dir.z >> 9) & 0x7f80u;  // record = metadata + coefficients
+    const bool cold = !(dir.z & kChunkHot);
+    unsigned long long* b = const_cast<unsigned long long*>(static_cast<const unsigned long long*>(bar));
+    mbar_expect_tx(b, bytes + (cold ? kXTileBytes : 0));
+    const unsigned long long src = ((unsigned long long)(unsigned)dir.y << 32 | (unsigned)dir.x) + (unsigned long long)((unsigned)o * bytes);
+    bulk_copy(const_cast<void*>(item), reinterpret_cast<const void*>(src), bytes, b);
+    if (cold) tma_load_2d(xs, xmap, dir.w, p0, b);
+}
+
 }  // namespace
 }  // namespace smx

@@ -347,39 +347,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 // One lane of the warp issues the copies of an item (lean kernel): the record size comes pre-computed in the directory.
 // The shared-memory directory of the lean kernel holds, per item: the global address of its first record (x, y), then
 // flags | nf << 8 | record size in 128-byte units << 16 | k-steps << 24 (z; bit 7 = last item of its warp), first column (w).
-constexpr int kDirLast = 0x80;
-__device__ __forceinline__ bool elect_one() {
-    unsigned pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-// Item buffer + its mbarrier; the two of a warp sit back to back, so ONE signed stride flips every pointer into them.
-// DEEP (hot parts of five to eight pairs): the record ends with a second factor list, factors 5..8 of every row slot,
-// which lands right behind the item's coefficients (at most at `fac2`).
-template <bool DEEP>
-struct alignas(16) LeanStage {
-    ItemBuffer item;
-    unsigned long long bar, pad;
-};
-template <>
-struct alignas(16) LeanStage<true> {
-    ItemBuffer item;
-    int4 fac2[16];
-    unsigned long long bar, pad;
-};
 static_assert(2 * sizeof(LeanStage<false>) <= sizeof(ItemStage) + 32, "the lean layout uses the alignment slack of the carve-up");
-template <bool DEEP>
-__host__ __device__ constexpr size_t lean_stage_bytes() { return DEEP ? 2 * sizeof(LeanStage<true>) : sizeof(ItemStage) + 32; }  // per warp
-__device__ __forceinline__ void stage_lean(const CUtensorMap* xmap, const void* item, const void* bar, double* xs, const int4 dir, int o, int p0) {
-    const unsigned bytes = ((unsigned)dir.z >> 9) & 0x7f80u;  // record = metadata + coefficients
-    const bool cold = !(dir.z & kChunkHot);
-    unsigned long long* b = const_cast<unsigned long long*>(static_cast<const unsigned long long*>(bar));
-    mbar_expect_tx(b, bytes + (cold ? kXTileBytes : 0));
-    const unsigned long long src = ((unsigned long long)(unsigned)dir.y << 32 | (unsigned)dir.x) + (unsigned long long)((unsigned)o * bytes);
-    bulk_copy(const_cast<void*>(item), reinterpret_cast<const void*>(src), bytes, b);
-    if (cold) tma_load_2d(xs, xmap, dir.w, p0, b);
-}
-
+static_assert(lean_stage_bytes<false>() <= sizeof(ItemStage) + 32, "smem_bytes() sizes the carve-up with ItemStage");
 template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP = false, bool ONE = false>
 __global__ void __launch_bounds__(NW * 32, 2)
 fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
@@ -554,6 +523,13 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     } else {
                         if (more && lane == 0) stage_lean(&xmap, ibt + flip, barp + flip, const_cast<double*>(xlo), ndir, o, p0);
                     }
+#ifdef SMX_TUNING
+                    if (!HOT && (a.ablate & 1) && ksteps == 1) {  // timing experiment: thin cold items stream x but compute nothing
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tot[i] += (q0[i].x + q0[i].y) + (q1[i].x + q1[i].y) + a0lo.x + b0.x;
+                        return;
+                    }
+#endif
 
                     double acc[4][2][2];
                     {
@@ -696,31 +672,43 @@ int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
 template <int NW>
 int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     if (d.deep) return d.eta0_zero ? launch_lean2<NW, true, false, true, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, true>(map, a, d, x, y, st);
-    static const int one = std::getenv("SMX_FAST_ONE") ? std::atoi(std::getenv("SMX_FAST_ONE")) : 1;  // tuning knob
+    static const int one = tune_int("SMX_FAST_ONE", 1);  // tuning knob
     if (one && a.d_out == 1) return d.eta0_zero ? launch_lean2<NW, true, false, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false, true>(map, a, d, x, y, st);
-    static const int elect = std::getenv("SMX_FAST_ELECT") ? std::atoi(std::getenv("SMX_FAST_ELECT")) : 1;  // tuning knob (measured: 1.847 vs 1.888 ms)
+    static const int elect = tune_int("SMX_FAST_ELECT", 1);  // tuning knob (measured: 1.847 vs 1.888 ms)
     if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false>(map, a, d, x, y, st);
     return d.eta0_zero ? launch_lean2<NW, true, false, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false, false>(map, a, d, x, y, st);
 }
 
 }  // namespace
 
+static int prepare_shape(FastDevice& d);
+
 // Chooses the CTA shape for this plan and opts into the shared memory it needs.
 int fast_kernel_prepare(FastDevice& d) {
+    const int rc = prepare_shape(d);
+    if (rc) return rc;
+    d.pipe_warps = 0;
+    if (d.flat && !d.deep && !d.multi) {  // single output: the pipelined kernel (smx_fast_pipe.cu) when its buffers fit
+        d.pipe_warps = 1;  // eligible; fast_upload() settles the number of workers
+    }
+    return SMX_OK;
+}
+
+static int prepare_shape(FastDevice& d) {
     if (encode_tiled() == nullptr) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     int device = 0, smem_optin = 0, smem_sm = 0;
     SMX_CUDA(cudaGetDevice(&device));
     SMX_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     int want = 0;
-    if (const char* env = std::getenv("SMX_FAST_WARPS")) want = std::atoi(env);  // tuning knob: 4, 8 or 12
+    want = tune_int("SMX_FAST_WARPS", 0);  // tuning knob: 4, 8 or 12
     const bool fits4 = 2 * (smem_bytes(d, 4) + 1024) <= (size_t)smem_sm;
     const bool fits8 = smem_bytes(d, 8) <= (size_t)smem_optin;
     const bool fits12 = smem_bytes(d, 12) <= (size_t)smem_optin;
     const bool fits16 = smem_bytes(d, 16) <= (size_t)smem_optin;
     // preferred: no product rows in the table (two CTAs of 8 or 6 warps per SM: the barriers and the prologue of one tile
     // overlap the main loop of another); needs a factor list for every row (hot parts of at most four pairs)
-    static const int want_flat = std::getenv("SMX_FAST_FLAT") ? std::atoi(std::getenv("SMX_FAST_FLAT")) : 1;
+    static const int want_flat = tune_int("SMX_FAST_FLAT", 1);
     d.flat = false;
     d.multi = 0;
     {   // a few outputs: several coefficient sets per pass (its warp count also fixes the per-warp item lists)
@@ -746,7 +734,7 @@ int fast_kernel_prepare(FastDevice& d) {
     // per-summand kernels).  Chosen when no variant with product rows fits in shared memory (SMX_FAST_DEEP=1: always).
     d.deep = false;
     if (!d.flat_ok && d.deep_ok && want_flat) {
-        static const int want_deep = std::getenv("SMX_FAST_DEEP") ? std::atoi(std::getenv("SMX_FAST_DEEP")) : -1;
+        static const int want_deep = tune_int("SMX_FAST_DEEP", -1);
         if (want_deep == 1 || (want_deep != 0 && !(fits4 || fits8 || fits12 || fits16))) {
             for (int nw : {8, 6}) {
                 if (2 * (lean_smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) {
@@ -789,13 +777,14 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     const cuuint32_t estr[2] = {1, 1};
     // L2 promotion: a tile row is 128 bytes; with 256-byte promotion the fetch also brings the same rows of the next column
     // block into L2 (another item of the same tile, a few microseconds later)
-    static const int promo = std::getenv("SMX_FAST_L2PROMO") ? std::atoi(std::getenv("SMX_FAST_L2PROMO")) : 256;  // (measured: 1.790 vs 1.799 ms)
+    static const int promo = tune_int("SMX_FAST_L2PROMO", 256);  // (measured: 1.790 vs 1.799 ms)
     const CUresult res = encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                         promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                         : promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
+    if (d.pipe_warps > 0 && !a.gradient && a.N < (1ll << 31) - kTile) return pipe_kernel_launch(map, d, a, x, y, st);
     if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
     if (d.flat) {
         if (a.gradient && d.deep) return fail(SMX_ERR_UNSUPPORTED, "eight-factor records: the fast path has no gradient kernel for them");
@@ -803,7 +792,7 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
         if (a.gradient && d.warps == 12) return launch<12, 1, 0, true, 2, true>(map, a, d, x, y, st);
         if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
         // values: the lean item loop (SMX_FAST_LEAN=0 selects the general kernel, for A/B timing)
-        static const int lean = std::getenv("SMX_FAST_LEAN") ? std::atoi(std::getenv("SMX_FAST_LEAN")) : 1;
+        static const int lean = tune_int("SMX_FAST_LEAN", 1);
         if (d.deep && a.N >= (1ll << 31) - kTile) return fail(SMX_ERR_UNSUPPORTED, "more than 2^31 points in one call");
         if ((lean || d.deep) && a.N < (1ll << 31) - kTile) {
             if (d.warps == 8) return launch_lean<8>(map, a, d, x, y, st);
@@ -822,12 +811,8 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
     if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
     if (d.warps == 16) {
-        static const int ablate = std::getenv("SMX_FAST_ABLATE") ? std::atoi(std::getenv("SMX_FAST_ABLATE")) : 0;
-        if (ablate == 1) return launch<16, 1, 1>(map, a, d, x, y, st);  // timing experiments, results are wrong on purpose
-        if (ablate == 2) return launch<16, 1, 2>(map, a, d, x, y, st);
-        if (ablate == 3) return launch<16, 1, 3>(map, a, d, x, y, st);
         // 16 warps leave 128 registers per thread: pre-loading one k-step (not two) keeps the kernel spill free (measured)
-        static const int early = std::getenv("SMX_FAST_EARLY") ? std::atoi(std::getenv("SMX_FAST_EARLY")) : 1;
+        static const int early = tune_int("SMX_FAST_EARLY", 1);
         if (early == 2) return launch<16, 1>(map, a, d, x, y, st);
         return launch<16, 1, 0, false, 1>(map, a, d, x, y, st);
     }

@@ -255,7 +255,7 @@ int launch_multi(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
 // and cfg4 tables: two sets x 12 warps and three sets x 8 warps gain 13-25 % for 2..6 outputs; beyond that the extra passes
 // with a partly filled last group and one CTA per SM eat the gain, and four sets x 6 warps are too few warps).
 bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* warps) {
-    static const int want = std::getenv("SMX_FAST_MULTI") ? std::atoi(std::getenv("SMX_FAST_MULTI")) : -1;  // 0: off; 2, 3: force
+    static const int want = tune_int("SMX_FAST_MULTI", -1);  // 0: off; 2, 3: force
     if (want == 0 || !d.flat_ok || d.d_out < 2 || d.d_out >= 32) return false;
     if (want < 0 && d.d_out > 6) return false;
     // (measured against one output per pass of the lean kernel, cfg2 tables, ms per 1e6 points: 2 outputs 3.46 vs 3.29,

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <thread>
@@ -92,6 +93,36 @@ std::vector<double> leja_order(const double* pts, int n) {
     return out;
 }
 
+// Largest absolute error of a cardinal function l_c(x) = prod_{j != c} (x - xi_j) / (xi_c - xi_j) when it is evaluated the
+// way the kernels do it - sum_k minv[k][c] pi_k(x) with the Newton products pi_k and the sum in fp64 - measured against the
+// product formula in long double on 48 uniform samples of the node span and the midpoints between neighbouring nodes.
+double newton_form_error(const double* nodes, const double* eta, int m, const std::vector<ld>& minv) {
+    std::vector<double> xs, sorted(nodes, nodes + m);
+    std::sort(sorted.begin(), sorted.end());
+    for (int i = 0; i <= 48; ++i) xs.push_back(sorted.front() + (sorted.back() - sorted.front()) * i / 48.0);
+    for (int i = 0; i + 1 < m; ++i) xs.push_back(0.5 * (sorted[i] + sorted[i + 1]));
+    std::vector<double> c((size_t)m * m), pi((size_t)m);
+    for (size_t i = 0; i < c.size(); ++i) c[i] = (double)minv[i];
+    double worst = 0.0;
+    for (double x : xs) {
+        pi[0] = 1.0;
+        for (int k = 1; k < m; ++k) pi[k] = pi[k - 1] * (x - eta[k - 1]);
+        for (int cidx = 0; cidx < m; ++cidx) {
+            double v = 0.0;
+            for (int k = 0; k < m; ++k) v = std::fma(c[(size_t)k * m + cidx], pi[k], v);
+            ld exact = 1.0L;
+            for (int j = 0; j < m; ++j)
+                if (j != cidx) exact *= ((ld)x - (ld)nodes[j]) / ((ld)nodes[cidx] - (ld)nodes[j]);
+            worst = std::max(worst, (double)fabsl((ld)v - exact));
+        }
+    }
+    return worst;
+}
+// Accepted loss (absolute, cardinal functions are O(1) between the nodes).  Nested Leja rules stay below 2e-14 up to degree
+// 150; Gauss-Hermite rules re-expressed on the Leja-ordered nodes of their highest degree pass up to degree ~14 (6e-15 at
+// degree 10, 1.5e-11 at 20, 5e-8 at 30).  Beyond the limit smx_create falls back to the per-summand barycentric kernels.
+constexpr double kNewtonErrorMax = 2.0e-13;
+
 // One summand (multi-index nu with zeta != 0), wherever its tables live: in the reference's padded per-group layout or
 // in the compact node-indexed form of smx_create_compact.
 struct Summand {
@@ -149,10 +180,7 @@ std::string compact_summands(int64_t d_out, const CompactView& cv, std::vector<S
 static std::string build_from_summands(int64_t d_in, int64_t d_out, const double* offset, std::vector<Summand>& summands,
                                        int64_t w_pad, FastPlan& plan, const PlanOptions& opt);
 
-std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
-                            FastPlan& plan, const PlanOptions& opt) {
-    std::vector<Summand> summands;
-    int64_t w_pad = 0;
+static std::string group_summands(int64_t d_out, const std::vector<GroupView>& groups, std::vector<Summand>& summands, int64_t& w_pad) {
     for (const GroupView& G : groups) {
         if (G.n <= 0 || G.n > kMaxLevels) return "group with unsupported number of active dimensions";
         if ((int)G.tau.size() != G.n) return "tau has wrong length";
@@ -176,6 +204,15 @@ std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, c
             summands.push_back(sm);
         }
     }
+    return "";
+}
+
+std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
+                            FastPlan& plan, const PlanOptions& opt) {
+    std::vector<Summand> summands;
+    int64_t w_pad = 0;
+    const std::string err = group_summands(d_out, groups, summands, w_pad);
+    if (!err.empty()) return err;
     return build_from_summands(d_in, d_out, offset, summands, w_pad, plan, opt);
 }
 
@@ -188,24 +225,26 @@ std::string build_fast_plan_compact(int64_t d_in, int64_t d_out, const double* o
 }
 
 // Smolyak quadrature of the summands in long double:  Q[o] = offset[o] + sum_s zeta_s sum_mu value(mu)[o] prod_j quad_j[mu_j]
-std::string integrate_compact(int64_t d_out, const double* offset, const CompactView& cv, std::vector<double>& Q) {
-    std::vector<Summand> summands;
-    const std::string err = compact_summands(d_out, cv, summands);
-    if (!err.empty()) return err;
+static std::string integrate_summands(int64_t d_out, const double* offset, const std::vector<Summand>& summands, std::vector<double>& Q) {
     std::vector<ld> acc((size_t)d_out, 0.0L);
     for (int64_t o = 0; o < d_out; ++o) acc[o] = offset ? (ld)offset[o] : 0.0L;
     for (const Summand& sm : summands) {
         int mu[kMaxLevels] = {0};
         int64_t count = 1;
         for (int j = 0; j < sm.n; ++j) {
-            if (!sm.quad[j]) return "no quadrature weights in the compact descriptor";
+            if (!sm.quad[j]) return "no quadrature weights in the descriptor";
             count *= sm.degs[j] + 1;
         }
         for (int64_t idx = 0; idx < count; ++idx) {
             ld w = (ld)sm.zeta;
-            for (int j = 0; j < sm.n; ++j) w *= (ld)sm.quad[j][mu[j]];
-            const double* v = sm.values + sm.vidx[idx] * sm.vstride;
-            for (int64_t o = 0; o < d_out; ++o) acc[o] += w * (ld)v[o];
+            int64_t foff = 0;
+            for (int j = 0; j < sm.n; ++j) w *= (ld)sm.quad[j][mu[j]], foff += mu[j] * sm.fstride[j];
+            if (sm.vidx) {
+                const double* v = sm.values + sm.vidx[idx] * sm.vstride;
+                for (int64_t o = 0; o < d_out; ++o) acc[o] += w * (ld)v[o];
+            } else {
+                for (int64_t o = 0; o < d_out; ++o) acc[o] += w * (ld)sm.F[o * sm.ostride + foff];
+            }
             for (int j = sm.n - 1; j >= 0; --j) {
                 if (++mu[j] <= sm.degs[j]) break;
                 mu[j] = 0;
@@ -215,6 +254,23 @@ std::string integrate_compact(int64_t d_out, const double* offset, const Compact
     Q.resize((size_t)d_out);
     for (int64_t o = 0; o < d_out; ++o) Q[o] = (double)acc[o];
     return "";
+}
+
+std::string integrate_compact(int64_t d_out, const double* offset, const CompactView& cv, std::vector<double>& Q) {
+    std::vector<Summand> summands;
+    const std::string err = compact_summands(d_out, cv, summands);
+    if (!err.empty()) return err;
+    return integrate_summands(d_out, offset, summands, Q);
+}
+
+static std::string group_summands(int64_t d_out, const std::vector<GroupView>& groups, std::vector<Summand>& summands, int64_t& w_pad);
+
+std::string integrate_groups(int64_t d_out, const double* offset, const std::vector<GroupView>& groups, std::vector<double>& Q) {
+    std::vector<Summand> summands;
+    int64_t w_pad = 0;
+    const std::string err = group_summands(d_out, groups, summands, w_pad);
+    if (!err.empty()) return err;
+    return integrate_summands(d_out, offset, summands, Q);
 }
 
 static std::string build_from_summands(int64_t d_in, int64_t d_out, const double* offset, std::vector<Summand>& summands,
@@ -275,6 +331,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     }
 
     // ---- 3. nodal values -> Newton coefficients, per pair -------------------------------------------------
+    std::map<std::vector<double>, double> cond_cache;  // (nodes, centres) -> error of the fp64 Newton form (pairs share node sets)
     for (PairInfo& p : pairs) {
         const int m = p.deg + 1;
         std::vector<ld> A((size_t)m * m);
@@ -287,6 +344,29 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             }
         }
         if (!invert(A, m, p.minv)) return "interpolation nodes of one slot are not distinct";
+        // The change of basis is exact in long double, but the kernels evaluate the Newton form in fp64: for non-nested
+        // rules of high degree (Gauss-Hermite beyond degree ~15) the Newton coefficients of the cardinal functions grow
+        // until their cancellation costs more digits than the path may lose.  Measure it: every cardinal function through
+        // its Newton form in fp64 against its product formula in long double, on samples over the span of the nodes.
+        if (m > 6) {
+            std::vector<double> key(p.nodes, p.nodes + m);
+            key.insert(key.end(), eta, eta + (m - 1));
+            auto it = cond_cache.find(key);
+            double err = 0.0;
+            if (it != cond_cache.end()) {
+                err = it->second;
+            } else {
+                err = newton_form_error(p.nodes, eta, m, p.minv);
+                cond_cache.emplace(std::move(key), err);
+            }
+            plan.newton_error = std::max(plan.newton_error, err);
+        }
+    }
+    if (plan.newton_error > kNewtonErrorMax) {
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "ill-conditioned: the hierarchical (Newton) form of a 1-D rule of this layout loses %.1e of a cardinal function in "
+                      "fp64 (limit %.1e)", plan.newton_error, kNewtonErrorMax);
+        return msg;
     }
 
     // ---- 4. enumerate terms: every mu <= nu of every summand ------------------------------------------------
@@ -717,6 +797,21 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         }
         i = j;
     }
+#ifdef SMX_TUNING
+    {   // timing experiments (results are WRONG on purpose; tuning builds only): drop classes of work items to measure what
+        // each class costs.  SMX_ABL_DROP bits: 1 = cold items of at most SMX_ABL_THIN_ROWS rows, 2 = other cold items, 4 = hot
+        const int drop = tune_int("SMX_ABL_DROP", 0), thin_rows = tune_int("SMX_ABL_THIN_ROWS", 4);
+        if (drop) {
+            std::vector<Chunk> kept;
+            for (Chunk& ck : chunks) {
+                const bool hot = ck.flags & kChunkHot, thin = !hot && (int)ck.rows.size() <= thin_rows && !(ck.flags & kChunkSplit);
+                const int cls = hot ? 4 : thin ? 1 : 2;
+                if (!(drop & cls)) kept.push_back(std::move(ck));
+            }
+            chunks.swap(kept);
+        }
+    }
+#endif
     // Order: big (FP64-heavy) and small (streaming) items alternate, so that every warp of a CTA always has both kinds
     // in flight (warp w takes items w, w + n_warps, ..).
     std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.rows.size() > b.rows.size(); });

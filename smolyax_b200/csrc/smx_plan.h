@@ -15,10 +15,31 @@
 // block across lanes, the points in registers, and the row products m_r in shared memory.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 namespace smx {
+
+// Tuning knobs are read from the environment ONLY in builds with -DSMX_TUNING (SMX_TUNING=1 python -m smolyax_b200._build,
+// used by benchmarks/ for A/B timing).  The product library ignores the environment: every knob has its measured default.
+inline int tune_int(const char* name, int dflt) {
+#ifdef SMX_TUNING
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+inline const char* tune_str(const char* name) {
+#ifdef SMX_TUNING
+    return std::getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 struct GroupView {
     int n = 0;
@@ -140,6 +161,7 @@ struct FastPlan {
     int64_t padded_fma = 0;              // FMAs per point and output the kernel executes: 32 per non-empty (k-step, half block)
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
     bool has_sparse = false;             // work items + coefficient sets above are filled
+    double newton_error = 0.0;           // worst fp64 error of a cardinal function through its Newton form (conditioning check)
 
     // Dense (GEMM-regime) form for large d_out:  y = c0 + Phi(x) C  with one column of Phi per term,
     // Phi[p][t] = tab[hot part of t][p] * pi_{leading entry of t}(x_p)  and  C (terms x d_out).  Terms are ordered hot
@@ -182,6 +204,8 @@ std::string build_fast_plan_compact(int64_t d_in, int64_t d_out, const double* o
                                     const PlanOptions& opt = PlanOptions());
 // Smolyak quadrature of a compact descriptor on the host, in long double (the integral does not depend on x).
 std::string integrate_compact(int64_t d_out, const double* offset, const CompactView& cv, std::vector<double>& Q);
+// same for the reference's per-group layout (needs the quadrature tables of the groups)
+std::string integrate_groups(int64_t d_out, const double* offset, const std::vector<GroupView>& groups, std::vector<double>& Q);
 
 // Verification aid for the CPU-only test-suite: evaluates the plan on the host in fp64 in the same order as
 // the kernel.  NOT a product path — nothing in smolyax_b200/ calls it; see tests/test_plan.py.

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (ALL_CASES, BIG_CASES, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double,
+from helpers import (ALL_CASES, BIG_CASES, ILL_CONDITIONED, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double,
                      scaled_error)
 
 pytestmark = pytest.mark.gpu
@@ -33,7 +33,8 @@ def test_values_fast_path(case):
     from oracle import oracle
 
     g, ip = _build(case)
-    assert ip.device_info()["has_fast_path"] == 1
+    # (a non-nested rule of high degree is refused by the plan compiler's conditioning check: per-summand kernels then)
+    assert ip.device_info()["has_fast_path"] == (0 if case in ILL_CONDITIONED else 1)
     x = g["x"]
     y = ip(x)
     assert isinstance(y, np.ndarray) and y.shape == g["y_ref"].shape
@@ -95,6 +96,8 @@ def test_gradient_barycentric_kernels_and_finite_option(case):
     ok = ~np.isnan(J_orc)
     scale = max(1.0, float(np.max(np.abs(J_orc[ok])))) if ok.any() else 1.0
     assert np.max(np.abs(J[ok] - J_orc[ok]), initial=0.0) <= 1e-10 * scale
+    if case in ILL_CONDITIONED:
+        return  # (no hierarchical form, hence no finite-at-nodes gradient: the handle runs the reference's arithmetic)
     _, fin = _build(case, nan_at_nodes=False)
     Jf = fin.gradient(x)
     assert np.isfinite(Jf).all()
@@ -184,7 +187,7 @@ def test_barycentric_module_functions():
 # ---------------------------------------------------------------------------------------------------------------------
 # GEMM-regime form (K2) and the compact create entry
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ALL_CASES)
+@pytest.mark.parametrize("case", [c for c in ALL_CASES if c not in ILL_CONDITIONED])
 def test_values_dense_path(case):
     """smx_eval through the dense term matrix + FP64 tensor instruction (forced here; chosen by itself for d_out >= 32):
     same bound against the reference as the block-sparse path, ragged batch sizes, bitwise repeatable."""

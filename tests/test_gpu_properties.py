@@ -252,12 +252,8 @@ def test_compact_create_rejects_malformed_descriptors_and_flags():
 
 def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
     """The lean block-sparse kernel: (a) a small batch spreads its outputs over gridDim.y, a large one walks them inside
-    the CTA - same bits either way; (b) the general kernel (SMX_FAST_LEAN=0, read once per process, so in a child
-    process) gives the same bits as the lean one; (c) non-zero first centres (custom Leja domain) take the variant
-    with the subtraction and still reproduce a polynomial exactly."""
-    import os
-    import subprocess
-    import sys
+    the CTA - same bits either way; (c) non-zero first centres (custom Leja domain) take the variant with the subtraction
+    and still reproduce a polynomial exactly.  (The kernels' tuning knobs are compiled out of the product library.)"""
 
     d_in, d_out = 24, 10  # below the GEMM regime: ten passes of the block-sparse kernel
     k = workloads.anisotropy(d_in)
@@ -271,24 +267,6 @@ def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
     y_small = ip(x[:1000])             # 32 tiles: outputs spread over gridDim.y
     assert torch.equal(y_small, y_big[:1000])
     assert torch.equal(ip(x[:33]), y_big[:33])
-    np.save("/tmp/_smx_knob_x.npy", x[:4096].cpu().numpy())
-    np.save("/tmp/_smx_knob_y.npy", y_big[:4096].cpu().numpy())
-    child = (
-        "import numpy as np, torch\n"
-        "from smolyax_b200 import indices, nodes, workloads\n"
-        "from smolyax_b200.interpolation import SmolyakBarycentricInterpolator\n"
-        f"d_in, d_out = {d_in}, {d_out}\n"
-        "k = workloads.anisotropy(d_in)\n"
-        "t = indices.find_approximate_threshold(k, 700, True)\n"
-        "ip = SmolyakBarycentricInterpolator(node_gen=nodes.Leja(dim=d_in), k=k, t=t, d_out=d_out,\n"
-        "                                    f=workloads.TargetFamily(d_in, d_out), batched_f=True)\n"
-        "y = ip(torch.from_numpy(np.load('/tmp/_smx_knob_x.npy')).cuda()).cpu().numpy()\n"
-        "assert np.array_equal(y, np.load('/tmp/_smx_knob_y.npy')), np.max(np.abs(y - np.load('/tmp/_smx_knob_y.npy')))\n"
-    )
-    env = dict(os.environ, SMX_FAST_LEAN="0", PYTHONPATH=os.pathsep.join([os.getcwd()] + sys.path))
-    out = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-
     # (c) custom domain: first centres != 0
     rng = np.random.default_rng(11)
     dom = np.stack([rng.uniform(-3, -1, 6), rng.uniform(0.5, 2, 6)], axis=1)
@@ -343,3 +321,88 @@ def test_tables_from_a_file_give_the_same_bits(tmp_path, mode):
     assert np.array_equal(np.isnan(J), np.isnan(J2))
     assert np.max(np.abs(np.nan_to_num(J) - np.nan_to_num(J2))) <= 1e-13 * max(1.0, float(np.nanmax(np.abs(J))))
     assert np.array_equal(ip.integral(), again.integral())
+
+
+@pytest.mark.parametrize("rule", ["leja", "gh"])
+def test_single_output_pipelined_kernel_ragged_batches_and_repeatability(rule):
+    """d_out = 1 runs the warp-specialised kernel (workers + service warp, csrc/smx_fast_pipe.cu): against the CPU oracle in the
+    summand-magnitude norm, for batch sizes below one tile, ragged, one tile per CTA and several tiles per CTA (the item
+    stream then crosses tile boundaries), and with the same bits run to run and whatever the batch the point sits in.
+    Gauss-Hermite takes the variant with non-zero first centres."""
+    from oracle import oracle
+
+    w = workloads.Workload("pipe", rule, 60, 1, 900, 0)
+    ip = _interp(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=1, f=w.target(), batched_f=True, layout="reference")
+    info = ip.device_info()
+    assert info["has_fast_path"] == 1 and info["has_dense_path"] == 0
+    n_big = 148 * 32 * 3 + 17
+    x = w.points(n_big, seed=5)
+    xd = torch.from_numpy(x).cuda()
+    y = ip(xd)
+    assert torch.equal(ip(xd), y)
+    sample = np.r_[0:200, n_big - 200:n_big]
+    layout = ip.reference_layout()
+    ref = oracle.evaluate(layout, x[sample])
+    mag = oracle.evaluate({k: (np.abs(v) if k.startswith("zetas_") or k == "offset" else v) for k, v in layout.items()}, x[sample])
+    assert np.max(np.abs(y.cpu().numpy()[sample] - ref) / np.abs(mag)) < 1e-12
+    for n in (1, 5, 31, 32, 33, 148 * 32, 148 * 32 + 1):
+        assert torch.equal(ip(xd[:n]), y[:n]), n
+    assert np.array_equal(ip(x[:1000]), y[:1000].cpu().numpy())  # host pipeline: same kernel, same bits
+
+
+def test_high_degree_gauss_hermite_falls_back_to_the_reference_arithmetic():
+    """Non-nested rules of high degree: the Newton form of the fast path would lose digits without any warning (at degree 40
+    more than the interpolation error).  The plan compiler measures that and refuses; the handle then evaluates with the
+    per-summand barycentric kernels and agrees with the oracle - values, gradient and integral - like any other."""
+    from oracle import oracle
+
+    gen = nodes.GaussHermite(dim=2)
+    k = [1.0, 10.0]
+    f = workloads.TargetFamily(2, 1)
+    for t, fast in ((9.5, 1), (41.5, 0)):
+        ip = _interp(node_gen=gen, k=k, t=t, d_out=1, f=f, layout="reference")
+        assert ip.device_info()["has_fast_path"] == fast, t
+        x = np.random.default_rng(3).standard_normal((300, 2)) / np.sqrt(2.0)
+        layout = ip.reference_layout()
+        y, ref = ip(x), oracle.evaluate(layout, x)
+        assert np.max(np.abs(y - ref)) < 1e-11 * max(1.0, float(np.max(np.abs(ref)))), t
+        J, J_ref = ip.gradient(x[:40]), oracle.gradient(layout, x[:40])
+        assert np.max(np.abs(J - J_ref)) < 1e-9 * max(1.0, float(np.max(np.abs(J_ref)))), t
+        assert np.max(np.abs(ip.integral() - oracle.integral(layout))) < 1e-11
+    # the compact form has no per-summand kernels behind it: refused with a message that says what to do
+    with pytest.raises(Exception, match="ill-conditioned"):
+        _interp(node_gen=gen, k=k, t=41.5, d_out=1, f=f, layout="compact")
+
+
+def test_more_than_eight_active_dimensions_per_summand():
+    """Summands with nine active dimensions (low d_in, high cardinality: |Lambda| ~ 5e4 and up, too slow to build in a test,
+    so the reference-layout arrays are written down directly): the per-summand kernels stop at eight, the fast path does
+    not - smx_create takes the layout all the same, values come from the fast path (eight-factor records), the integral
+    from the host at create time; the gradient of such a handle is refused (SMX_ERR_UNSUPPORTED), not wrong."""
+    from oracle import oracle
+    from smolyax_b200.interpolation import _host_weights
+
+    rng = np.random.default_rng(7)
+    d_in, d_out = 12, 2
+    layout = {"offset": rng.standard_normal(d_out)}
+    pts = np.array([0.0, 1.0])
+    for n, nn in ((2, 5), (9, 3)):
+        layout[f"F_{n}"] = rng.standard_normal((nn, d_out) + (2,) * n)
+        layout[f"nodes_{n}"] = np.tile(pts, (nn, n, 1))
+        layout[f"weights_{n}"] = np.tile(_host_weights(pts), (nn, n, 1))
+        layout[f"quad_{n}"] = np.tile(np.array([0.75, 0.25]), (nn, n, 1))
+        layout[f"dims_{n}"] = np.stack([np.sort(rng.choice(d_in, n, replace=False)) for _ in range(nn)]).astype(np.int64)
+        layout[f"degs_{n}"] = np.ones((nn, n), dtype=np.int64)
+        layout[f"zetas_{n}"] = rng.integers(-3, 4, nn).astype(np.int64)
+    ip = _interp(node_gen=nodes.Leja(dim=d_in), k=[1.0] * d_in, t=1.5, d_out=d_out)
+    ip.set_layout(layout)
+    info = ip.device_info()
+    assert info["has_fast_path"] == 1 and info["has_groups"] == 0
+    x = rng.uniform(-1, 1, (300, d_in))
+    ref = oracle.evaluate(layout, x)
+    assert np.max(np.abs(ip(x) - ref)) < 1e-12 * max(1.0, float(np.max(np.abs(ref))))
+    assert np.max(np.abs(ip.integral() - oracle.integral(layout))) < 1e-12 * max(1.0, float(np.max(np.abs(oracle.integral(layout)))))
+    from smolyax_b200._lib import SmolyaxCudaError
+
+    with pytest.raises(SmolyaxCudaError, match="unsupported"):
+        ip.gradient(x[:8])

@@ -7,7 +7,7 @@ import pytest
 
 from smolyax_b200 import _build
 from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
-from helpers import ALL_CASES, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double, scaled_error
+from helpers import ALL_CASES, ILL_CONDITIONED, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double, scaled_error
 
 
 class _Group(ctypes.Structure):
@@ -123,6 +123,9 @@ def test_plan_reproduces_reference_values(case):
         kwargs, f = interpolator_inputs(g)
         layout, _ = SmolyakBarycentricInterpolator(**kwargs)._assemble(f, {})
     plan = Plan(layout, g["x"].shape[1], int(g["d_out"]))
+    if case in ILL_CONDITIONED:  # refused, loudly: smx_create falls back to the per-summand kernels
+        assert plan.error is not None and plan.error.startswith("ill-conditioned"), plan.error
+        return
     assert plan.error is None, plan.error
     y = plan(g["x"])
     # parity with the reference: within 1e-12 of the summand magnitude (the reference's own rounding noise is larger)
@@ -149,6 +152,8 @@ def test_plan_gradient_sets_reproduce_reference_gradients(case):
     else:
         kwargs, f = interpolator_inputs(g)
         layout, _ = SmolyakBarycentricInterpolator(**kwargs)._assemble(f, {})
+    if case in ILL_CONDITIONED:
+        pytest.skip("the plan compiler refuses this layout (conditioning check): no derivative sets")
     J_ref = g["J_ref"]
     x = g["x"][: len(J_ref)]
     J = Plan(layout, x.shape[1], int(g["d_out"])).gradient(x)
@@ -186,7 +191,10 @@ def test_plan_rejects_malformed_layouts():
     assert "distinct" in Plan(bad, g["x"].shape[1], int(g["d_out"])).error
 
 
-@pytest.mark.parametrize("case", ALL_CASES)
+WELL_CONDITIONED = [c for c in ALL_CASES if c not in ILL_CONDITIONED]
+
+
+@pytest.mark.parametrize("case", WELL_CONDITIONED)
 def test_dense_form_reproduces_reference_values(case):
     """The GEMM-regime form (one column of Phi per term, dense coefficient matrix in DMMA fragment order) evaluated on
     the host in the kernel's order agrees with the reference outputs like the block-sparse form does."""
@@ -200,7 +208,7 @@ def test_dense_form_reproduces_reference_values(case):
     assert scaled_error(y, Plan(layout, d_in, d_out)(g["x"]), g["cond_abs"]) < 1e-13
 
 
-@pytest.mark.parametrize("case", LAYOUT_CASES)
+@pytest.mark.parametrize("case", [c for c in LAYOUT_CASES if c not in ILL_CONDITIONED])
 def test_compact_layout_gives_the_same_plan(case):
     """smx_create_compact's description (exact shapes, node-indexed values) compiles to the same coefficients as the
     reference's padded per-group layout, and its host quadrature equals the reference integral."""
@@ -236,7 +244,7 @@ def test_compact_layout_reuses_f_evals():
     assert again.n_f_evals_new == 0 and layout["values"].shape[0] in (again.n_f_evals, again.n_f_evals - 1)
 
 
-@pytest.mark.parametrize("case", ALL_CASES)
+@pytest.mark.parametrize("case", WELL_CONDITIONED)
 def test_dense_gradient_columns_match_the_sparse_sets(case):
     """Derivative sets as columns of the dense product (hot dimensions) + block-sparse row sums (cold dimensions):
     the same Jacobian as with block-sparse derivative sets, up to the summation order."""
