@@ -122,3 +122,31 @@ def integral(layout):
         lib().smo_group_integral(keep[0][1], keep[1][1], keep[2][1], ctypes.c_int64(len(keep[2][0])), ctypes.c_int(n),
                                  keep[3][1], ctypes.c_int64(d_out), Q.ctypes.data_as(_dp))
     return Q
+
+
+def _referee(layout, x, fn, shape_tail):
+    x_, px = _d(np.atleast_2d(x))
+    N, d_in = x_.shape
+    ns = group_sizes(layout)
+    d_out = int(np.asarray(layout["F_%d" % ns[0]]).shape[1]) if ns else len(layout["offset"])
+    assert np.dtype(np.longdouble).itemsize == 16 and np.finfo(np.longdouble).nmant == 63, "needs x87 80-bit long double"
+    out = np.zeros((N, d_out) + ((d_in,) if shape_tail else ()), dtype=np.longdouble)
+    if not shape_tail:
+        out += np.asarray(layout["offset"], dtype=np.float64).astype(np.longdouble)
+    for n in ns:
+        keep = [_d(layout[f"F_{n}"]), _d(layout[f"nodes_{n}"]), _d(layout[f"weights_{n}"]), _i(layout[f"dims_{n}"]),
+                _i(layout[f"degs_{n}"]), _i(layout[f"zetas_{n}"]), _i(_tau(layout, n))]
+        args = [px, ctypes.c_int64(N), ctypes.c_int64(d_in)] + ([ctypes.c_int64(d_in)] if shape_tail else []) + [k[1] for k in keep[:6]] + \
+               [ctypes.c_int64(len(keep[5][0])), ctypes.c_int(n), keep[6][1], ctypes.c_int64(d_out), ctypes.c_void_p(out.ctypes.data)]
+        getattr(lib(), fn)(*args)
+    return out
+
+
+def evaluate_referee(layout, x):
+    """``evaluate`` carried out in 80-bit long double on the same fp64 tables (accuracy referee)."""
+    return _referee(layout, x, "smo_group_eval_ld", False)
+
+
+def gradient_referee(layout, x):
+    """``gradient`` carried out in 80-bit long double (NaN at node hits, like the fp64 version)."""
+    return _referee(layout, x, "smo_group_gradient_ld", True)

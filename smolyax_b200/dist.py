@@ -144,3 +144,41 @@ def max_over_ranks(value: float) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=_device_for_backend())
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this process (and therefore the page-locked buffers it allocates afterwards: first touch) to the CPUs of the NUMA
+    node its GPU hangs off, when the box has more than one node.  Returns what was found, for the bench line.  The end-to-end
+    path of several ranks shares the host's PCIe / memory complex; on a box whose GPUs all report the same node there is
+    nothing to separate, and the record says so."""
+    import os
+
+    out = {"gpu_numa_node": None, "nodes": None, "bound_cpus": None}
+    try:
+        import torch
+
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            bdf = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:  # NVML prints a 32-bit PCI domain, sysfs a 16-bit one
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        out["gpu_numa_node"], out["nodes"] = node, len(nodes)
+        if node >= 0 and len(nodes) > 1 and hasattr(os, "sched_setaffinity"):
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                out["bound_cpus"] = len(cpus)
+    except Exception as exc:  # (containers without sysfs access, ...): reported, never fatal
+        out["error"] = f"{type(exc).__name__}: {exc}"[:120]
+    return out

@@ -21,10 +21,25 @@ from typing import Callable, Sequence
 import numpy as np
 import torch
 
-from . import _lib, indices, nodes  # noqa: F401
+from . import indices, nodes  # noqa: F401
+
+
+class _Native:
+    """``libsmolyax_b200.so`` (ctypes binding ``_lib``), loaded at the first use of a device entry point.  The host half of
+    ``set_f`` (``_assemble``: tables as NumPy arrays) needs no GPU and no CUDA library - the reference arm of ``bench.py``
+    and the golden generator use it that way.  Every compute path goes through here and fails loudly if the library
+    cannot be loaded or built: there is no CPU fallback."""
+
+    def __getattr__(self, name):
+        from . import _lib as real
+
+        return getattr(real, name)
+
+
+_lib = _Native()
 
 _CODE = 1 << 20  # (dim, deg) -> dim * _CODE + deg
-_GRAD_COLUMN_BLOCK = 1024  # outputs per set of derivative tables when one handle cannot hold them for every output
+_GRAD_COLUMN_BLOCK = 1024  # most outputs per set of derivative tables when one handle cannot hold them for every output
 
 
 def _host_weights(pts: np.ndarray) -> np.ndarray:
@@ -94,7 +109,9 @@ class SmolyakBarycentricInterpolator:
         f : callable, optional
             Target function, called with one point ``(d_in,)``; see :meth:`set_f`.
         n_inputs : int, optional
-            Expected batch size; used to size the staging buffers of the host pipeline ahead of the first call.
+            Expected batch size.  Like the reference (interpolation.py:250-251: a warm-up call on ``n_inputs`` random points
+            at the end of ``set_f``), ``set_f`` then sizes the staging buffers of the host pipeline for that batch
+            (``smx_prepare``) and runs one evaluation of ``n_inputs`` points, so that the first timed call pays neither.
         memory_limit : float
             Accepted for compatibility.  The fused kernels have no per-summand intermediates, so nothing is batched.
         method : {"auto", "barycentric"}
@@ -149,9 +166,12 @@ class SmolyakBarycentricInterpolator:
 
     def _release(self):
         handle, self._handle = getattr(self, "_handle", None), None
-        lib = getattr(_lib, "lib", None) if _lib is not None else None  # (module globals are torn down at interpreter exit)
-        if handle is not None and lib is not None:
-            lib.smx_destroy(handle)
+        if handle is None:
+            return
+        try:  # (module globals are torn down at interpreter exit)
+            _lib.lib.smx_destroy(handle)  # puts the caller's current CUDA device back (DeviceGuard in smx_api.cu)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ set_f (interpolation.py:115-239)
     def set_f(self, *, f: Callable, f_evals: dict = None) -> dict:
@@ -192,6 +212,12 @@ class SmolyakBarycentricInterpolator:
             else:
                 flags |= _lib.SMX_KEEP_GROUPS | (_lib.SMX_NO_FAST_PATH if self._method == "barycentric" else 0)
                 self._handle = _lib.create(layout, self._d_in, self._d_out, flags, self._device)
+            if self._n_inputs:  # the reference's warm-up (interpolation.py:250-251): buffers sized, kernels loaded
+                n = int(self._n_inputs)
+                _lib.check(_lib.lib.smx_prepare(self._handle, n), "smx_prepare")
+                warm = torch.rand((n, self._d_in), dtype=torch.float64, device=f"cuda:{self._device}")
+                y = torch.empty((n, self._d_out), dtype=torch.float64, device=warm.device)
+                _lib.check(_lib.lib.smx_eval(self._handle, warm.data_ptr(), n, self._d_in, y.data_ptr(), self._stream()), "smx_eval")
 
     def save_layout(self, path) -> None:
         """Write the tables ``set_f`` assembled to ``path`` (``.npz``), so that another process or a later run can build
@@ -535,7 +561,7 @@ class SmolyakBarycentricInterpolator:
             xd = x if kind == "cuda" else (x.cuda() if kind == "torch_cpu" else torch.from_numpy(x).cuda())
             J = torch.empty((n_points, self._d_out, self._d_in), dtype=torch.float64, device=xd.device)
             status = _lib.lib.smx_gradient(self._handle, xd.data_ptr(), n_points, self._ldx(xd), J.data_ptr(), self._stream())
-            if status == _lib.SMX_ERR_UNSUPPORTED and self._layout.get("compact") and self._d_out > _GRAD_COLUMN_BLOCK:
+            if status == _lib.SMX_ERR_UNSUPPORTED and self._layout.get("compact") and self._d_out > 1:
                 self._gradient_by_columns(xd, J)  # derivative sets of all outputs at once were not built (d_out too large)
             else:
                 _lib.check(status, "smx_gradient")
@@ -544,19 +570,31 @@ class SmolyakBarycentricInterpolator:
             return J.cpu() if kind == "torch_cpu" else J.cpu().numpy()
 
     def _gradient_by_columns(self, xd, J) -> None:
-        """Gradient of a handle too wide for one set of derivative tables (compact layout, ``d_out`` in the thousands):
-        the interpolant is linear in ``f``, so ``J[:, lo:hi, :]`` is the gradient of the interpolant of outputs
-        ``lo:hi`` alone.  One temporary handle per block of ``_GRAD_COLUMN_BLOCK`` outputs (its derivative sets are
-        built, used once and freed: the tables of all blocks together are what did not fit)."""
+        """Gradient of a handle too wide for one set of derivative tables (compact layout, many outputs): the interpolant is
+        linear in ``f``, so ``J[:, lo:hi, :]`` is the gradient of the interpolant of outputs ``lo:hi`` alone.  One
+        temporary handle per block of outputs (its derivative sets are built, used once and freed: the tables of all blocks
+        together are what did not fit).  The block width starts at ``_GRAD_COLUMN_BLOCK`` and is halved until the
+        library accepts it (the derivative tables grow with terms x hot dimensions x outputs)."""
         from .dist import column_slice
 
-        for lo in range(0, self._d_out, _GRAD_COLUMN_BLOCK):
-            hi = min(lo + _GRAD_COLUMN_BLOCK, self._d_out)
+        width = min(_GRAD_COLUMN_BLOCK, max(1, self._d_out // 2))
+        lo = 0
+        while lo < self._d_out:
+            hi = min(lo + width, self._d_out)
             block = SmolyakBarycentricInterpolator(node_gen=self._node_gen, k=self._k, t=self._t, d_out=hi - lo,
                                                    device=self._device, nan_at_nodes=self._nan_at_nodes, layout="compact")
             block.set_layout(column_slice(self._layout, lo, hi))
-            J[:, lo:hi, :] = block.gradient(xd)
+            Jb = torch.empty((xd.shape[0], hi - lo, self._d_in), dtype=torch.float64, device=xd.device)
+            status = _lib.lib.smx_gradient(block._handle, xd.data_ptr(), xd.shape[0], self._ldx(xd), Jb.data_ptr(), self._stream())
+            if status == _lib.SMX_ERR_UNSUPPORTED and width > 1:
+                block._release()
+                width = max(1, width // 2)
+                continue
+            _lib.check(status, "smx_gradient")
+            J[:, lo:hi, :] = Jb
+            torch.cuda.current_stream().synchronize()  # the block's tables are freed next
             block._release()
+            lo = hi
 
     # ------------------------------------------------------------------ integral (interpolation.py:347-390)
     def integral(self):

@@ -377,8 +377,8 @@ def test_high_degree_gauss_hermite_falls_back_to_the_reference_arithmetic():
 def test_more_than_eight_active_dimensions_per_summand():
     """Summands with nine active dimensions (low d_in, high cardinality: |Lambda| ~ 5e4 and up, too slow to build in a test,
     so the reference-layout arrays are written down directly): the per-summand kernels stop at eight, the fast path does
-    not - smx_create takes the layout all the same, values come from the fast path (eight-factor records), the integral
-    from the host at create time; the gradient of such a handle is refused (SMX_ERR_UNSUPPORTED), not wrong."""
+    not - smx_create takes the layout all the same, values come from the fast path, the integral from the host at create
+    time; the gradient is either computed by the fast path or refused (SMX_ERR_UNSUPPORTED), never silently wrong."""
     from oracle import oracle
     from smolyax_b200.interpolation import _host_weights
 
@@ -404,5 +404,10 @@ def test_more_than_eight_active_dimensions_per_summand():
     assert np.max(np.abs(ip.integral() - oracle.integral(layout))) < 1e-12 * max(1.0, float(np.max(np.abs(oracle.integral(layout)))))
     from smolyax_b200._lib import SmolyaxCudaError
 
-    with pytest.raises(SmolyaxCudaError, match="unsupported"):
-        ip.gradient(x[:8])
+    try:  # refused (no derivative sets for eight-factor records) or right - never silently wrong
+        J = ip.gradient(x[:64])
+    except SmolyaxCudaError as exc:
+        assert "unsupported" in str(exc)
+    else:
+        J_ref = oracle.gradient(layout, x[:64])
+        assert np.max(np.abs(J - J_ref)) < 1e-11 * max(1.0, float(np.max(np.abs(J_ref))))

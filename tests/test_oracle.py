@@ -5,7 +5,7 @@ import pytest
 
 from oracle import oracle
 from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
-from helpers import BIG_CASES, LAYOUT_CASES, golden_layout, interpolator_inputs, load, scaled_error
+from helpers import BIG_CASES, LAYOUT_CASES, golden_layout, interpolator_inputs, load, long_double, scaled_error
 
 
 def _check(layout, g, tol_scaled):
@@ -47,3 +47,23 @@ def test_oracle_weights():
     diffs = pts[:, None] - pts
     diffs[diffs == 0] = 1
     assert np.allclose(oracle.compute_weights(pts), np.prod(1 / diffs, axis=0), rtol=1e-14)
+
+
+@pytest.mark.parametrize("case", LAYOUT_CASES)
+def test_long_double_referee_reproduces_the_reference_in_80_bit(case):
+    """oracle.evaluate_referee / gradient_referee (the C restatement carried out in long double) against the golden outputs
+    of the UNMODIFIED reference run in 80-bit arithmetic on the NumPy jax stand-in (oracle/make_golden.py): equal to a few
+    units of the long-double precision, same NaN pattern - so bench.py may use it as the accuracy referee at any size."""
+    from oracle import oracle
+
+    g = load(case)
+    layout = golden_layout(g)
+    y = oracle.evaluate_referee(layout, g["x"])
+    y_gold = long_double(g, "y")
+    assert float(np.max(np.abs(y - y_gold))) <= 1e-15 * max(1.0, float(np.max(np.abs(g["y_ref"]))))
+    J_gold = long_double(g, "J")
+    J = oracle.gradient_referee(layout, g["x"][: len(J_gold)])
+    ok = ~np.isnan(g["J_ref"])
+    assert np.array_equal(np.isnan(J.astype(float)), ~ok)
+    if ok.any():
+        assert float(np.max(np.abs((J - J_gold)[ok]))) <= 1e-14 * max(1.0, float(np.max(np.abs(g["J_ref"][ok]))))
