@@ -84,7 +84,7 @@ def main():
         if n_grad:
             xg = x[:n_grad]
             ms = timed(lambda: ip.gradient(xg), max(2, args.reps // 2))
-            lines.append({**base, "op": "gradient", "kernel": "dense" if info["dense_grad_columns"] else "sparse", "points": n_grad,
+            lines.append({**base, "op": "gradient", "kernel": "jobs" if info["grad_jobs"] else "per-summand", "points": n_grad,
                           "ms": ms, "value": n_grad * wl.d_out * wl.d_in / ms * 1e3, "unit": "J entries/s",
                           "points_per_s": n_grad / ms * 1e3, "j_write_gbs": 8.0 * n_grad * wl.d_out * wl.d_in / ms / 1e6})
         ms = timed(lambda: ip.integral(), args.reps)

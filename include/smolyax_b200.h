@@ -59,8 +59,7 @@ typedef struct {
                                        node, instead of the NaN the reference produces there (barycentric.py:152-154) */
 
 #define SMX_DENSE_PATH 8u     /* build the GEMM-regime form (dense term matrix, FP64 tensor instruction) even for small d_out */
-#define SMX_NO_DENSE_PATH 16u /* never build it; default: values use it when d_out >= 32, the gradient when there are at
-                                 least 32 derivative columns (d_out x hot dimensions)  (DESIGN.md "K2") */
+#define SMX_NO_DENSE_PATH 16u /* never build it; default: values use it when d_out >= 32  (DESIGN.md "K2") */
 
 typedef struct {
     int64_t d_in;
@@ -168,8 +167,9 @@ typedef struct {
     int32_t has_fast_path, has_groups, nested;
     int32_t has_dense_path; /* GEMM-regime form present: smx_eval uses it */
     int64_t dense_terms;    /* its K (terms, padded to whole stages of 64) */
-    int64_t dense_grad_columns; /* > 0: smx_gradient computes that many derivative sets (d_out x hot dimensions) as columns
-                                   of the same dense product */
+    int64_t grad_jobs;      /* > 0: smx_gradient runs the fast path - that many jobs per tile and output (one per cold block of 16
+                               columns of J, one per hot dimension) .. */
+    int64_t grad_items;     /* .. of that many work items in all */
 } smx_info;
 int smx_get_info(const smx_interp* h, smx_info* info);
 

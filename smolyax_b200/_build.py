@@ -22,7 +22,7 @@ HOST_LIB = PKG / "libsmolyax_host.so"
 CUDA_LIB = PKG / "libsmolyax_b200.so"
 
 HOST_SOURCES = ["smx_host.cpp", "smx_plan.cpp"]
-CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu", "smx_fast_kernel.cu", "smx_fast_pipe.cu", "smx_fast_multi.cu", "smx_dense_kernel.cu", "smx_plan.cpp"]
+CUDA_SOURCES = ["smx_api.cu", "smx_seam.cu", "smx_fast.cu", "smx_fast_kernel.cu", "smx_fast_pipe.cu", "smx_grad_kernel.cu", "smx_fast_multi.cu", "smx_dense_kernel.cu", "smx_plan.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -66,7 +66,7 @@ class Info(ctypes.Structure):
     _fields_ = [(name, c_int64) for name in (
         "d_in", "d_out", "n_summands", "w_raw", "w_pad", "n_terms", "n_entries", "n_rows", "n_chunks", "padded_fma",
         "device_bytes")] + [(name, c_int32) for name in ("has_fast_path", "has_groups", "nested", "has_dense_path")] + [
-        ("dense_terms", c_int64), ("dense_grad_columns", c_int64)]
+        ("dense_terms", c_int64), ("grad_jobs", c_int64), ("grad_items", c_int64)]
 
 
 EXPORTS = {

@@ -34,6 +34,7 @@ struct smx_interp {
     bool no_groups_by_depth = false;  // reference layout not uploaded: a summand has more active dimensions than the per-summand kernels take
     double* d_integral = nullptr;  // compact handles: the integral, computed at create time
     FastDevice fast;
+    GradDevice grad;  // gradient jobs of the fast path (present when the plan could build them)
     std::vector<SeamGroup> groups;
     std::vector<void*> owned;  // device allocations behind `groups`
     double* d_offset = nullptr;
@@ -99,6 +100,7 @@ void release(smx_interp* h) {
     DeviceGuard guard;
     cudaSetDevice(h->device);
     fast_free(h->fast);
+    grad_free(h->grad);
     for (void* p : h->owned) cudaFree(p);
     if (h->d_offset) cudaFree(h->d_offset);
     if (h->d_integral) cudaFree(h->d_integral);
@@ -134,7 +136,6 @@ PlanOptions plan_options(uint32_t flags, int64_t d_out, bool sparse_wanted) {
     // only costs memory once the dense form exists (it would still serve the gradient)
     opt.sparse = sparse_wanted && !(opt.dense && d_out > 2048);
     opt.gradient = opt.sparse;
-    opt.dense_gradient = (flags & SMX_NO_DENSE_PATH) ? 0 : (flags & SMX_DENSE_PATH) ? 1 : -1;
     return opt;
 }
 
@@ -155,7 +156,11 @@ int adopt_plan(smx_interp* h, const FastPlan& plan) {
     h->info.device_bytes += h->fast.bytes;
     h->info.has_dense_path = h->fast.has_dense;
     h->info.dense_terms = 4ll * h->fast.dense_k4;
-    h->info.dense_grad_columns = h->fast.has_dense_grad ? h->d_out * h->fast.n_gd : 0;
+    const int rcg = grad_upload(plan, h->fast, h->grad);
+    if (rcg) return rcg;
+    h->info.device_bytes += h->grad.bytes;
+    h->info.grad_jobs = h->grad.present ? h->grad.n_jobs : 0;
+    h->info.grad_items = h->grad.present ? h->grad.n_items : 0;
     return SMX_OK;
 }
 
@@ -268,6 +273,7 @@ int smx_create(const smx_interp_desc* desc, int device, smx_interp** out) {
         if (ill) set_error("smx_create: " + err);
         if (rc == SMX_ERR_UNSUPPORTED) {
             fast_free(h->fast);  // fall back to the per-summand kernels; still a CUDA path
+            grad_free(h->grad);
             want_groups = true;
         } else if (rc) {
             return rc;
@@ -354,7 +360,7 @@ int smx_gradient(smx_interp* h, const double* x, int64_t N, int64_t ldx, double*
     if (N == 0) return SMX_OK;
     if (!x || !J || ldx < h->d_in) return fail(SMX_ERR_INVALID_ARG, "smx_gradient: null buffer or ldx < d_in");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->has_fast && h->fast.has_sparse && h->fast.grad_ok) return fast_gradient(h->fast, x, N, ldx, J, !h->grad_finite, st);
+    if (h->has_fast && h->grad.present) return fast_gradient(h->fast, h->grad, x, N, ldx, J, !h->grad_finite, st);
     if (h->compact)
         return fail(SMX_ERR_UNSUPPORTED, "smx_gradient: the derivative coefficient sets of this handle were not built (d_out too large)");
     if (h->no_groups_by_depth)

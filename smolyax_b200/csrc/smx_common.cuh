@@ -82,9 +82,6 @@ struct FastDevice {
     int32_t* chunk_meta = nullptr;
     double* coef = nullptr;
     double* c0 = nullptr;
-    int32_t n_sets = 0, n_gd = 0;   // coefficient sets per row slot; hot dimensions with a derivative set
-    bool grad_ok = false;           // the plan carries derivative sets (or needs none): smx_gradient can use the fast path
-    int32_t* grad_dims = nullptr;
     int32_t* nan_off = nullptr;     // per dimension: the nodes at which the reference returns NaN gradients
     double* nan_nodes = nullptr;
     // GEMM-regime form (large d_out): dense term matrix in DMMA fragment order, see smx_plan.h
@@ -95,10 +92,6 @@ struct FastDevice {
     double* dense_coef = nullptr;
     bool eta0_zero = true;          // every cold block has zero first centres (pi_{j,1} = x_j): kernel variant without the subtraction
     bool has_cold = false;          // some leading entries live on cold columns (their derivatives are block-sparse row sums)
-    bool has_dense_grad = false;    // derivative sets as dense columns: smx_gradient = sparse kernel (cold columns) + dense kernel
-    double* dense_grad_coef = nullptr;
-    double* dense_grad_c0 = nullptr;
-    int32_t* dense_grad_col = nullptr;
     int64_t bytes = 0;
     int sm_count = 148;
     int warps = 12;  // warps per CTA of the evaluation kernel (12 or 8: one CTA per SM; 4: two CTAs per SM)
@@ -111,10 +104,29 @@ struct FastDevice {
     int32_t pipe_warp_off[17] = {0};  // .. on their own per-warp item lists
     int32_t* pipe_dir = nullptr;
 };
+// Gradient jobs on the device (smx_grad_kernel.cu; built by grad_upload from FastPlan::grad)
+struct GradDevice {
+    bool present = false;
+    double* records = nullptr;   // per (item, output): metadata + coefficients packed as DMMA B fragments
+    int32_t* dir = nullptr;      // 4 ints per item, in the order of the warps' job lists
+    int32_t* jobs = nullptr;     // 4 ints per job
+    double* job_c0 = nullptr;    // [job][d_out]
+    double* job_nodes = nullptr; // 32 doubles per cold job
+    int32_t* zero_cols = nullptr;
+    int32_t n_items = 0, n_jobs = 0, n_zero = 0;
+    int warps = 0;
+    int32_t warp_off[17] = {0};
+    int64_t bytes = 0;
+};
 int fast_upload(const FastPlan& plan, FastDevice& dev);
+int grad_upload(const FastPlan& plan, const FastDevice& dev, GradDevice& g);
+void grad_free(GradDevice& g);
+int grad_kernel_warps(const GradDevice& g, const FastDevice& d, int smem_sm);
+int grad_kernel_launch(const FastDevice& d, const GradDevice& g, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes,
+                       cudaStream_t st);
 void fast_free(FastDevice& dev);
 int fast_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
 int dense_eval(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st);
-int fast_gradient(const FastDevice& dev, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st);
+int fast_gradient(const FastDevice& dev, const GradDevice& g, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st);
 
 }  // namespace smx

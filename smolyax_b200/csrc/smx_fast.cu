@@ -83,8 +83,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     if ((rc = upload(plan.nan_off, &dev.nan_off, dev.bytes, 2))) return rc;
     if ((rc = upload(plan.nan_nodes, &dev.nan_nodes, dev.bytes))) return rc;
     // (the kernel addresses the dense matrix with 32-bit element offsets)
-    if ((plan.has_dense || plan.has_dense_grad) && dense_kernel_fits(plan.n_tab, smem_optin) &&
-        plan.dense_coef.size() < (size_t)UINT32_MAX && plan.dense_grad_coef.size() < (size_t)UINT32_MAX) {
+    if (plan.has_dense && dense_kernel_fits(plan.n_tab, smem_optin) && plan.dense_coef.size() < (size_t)UINT32_MAX) {
         dev.dense_k4 = plan.dense_k4;
         if ((rc = upload(plan.dense_meta, &dev.dense_meta, dev.bytes, 2))) return rc;
         if ((rc = upload(plan.dense_eta0, &dev.dense_eta0, dev.bytes))) return rc;
@@ -92,15 +91,8 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
             if ((rc = upload(plan.dense_coef, &dev.dense_coef, dev.bytes))) return rc;
             dev.has_dense = true;
         }
-        if (plan.has_dense_grad && sparse_ok) {  // (the cold columns of J come from the block-sparse kernel)
-            if ((rc = upload(plan.dense_grad_coef, &dev.dense_grad_coef, dev.bytes))) return rc;
-            if ((rc = upload(plan.dense_grad_c0, &dev.dense_grad_c0, dev.bytes))) return rc;
-            if ((rc = upload(plan.dense_grad_col, &dev.dense_grad_col, dev.bytes))) return rc;
-            dev.has_dense_grad = true;
-        }
     }
-    // (else: the product table is too large for the GEMM-regime kernel.  Values run the block-sparse kernel, one output per
-    // pass; if the derivative sets were only built as dense columns, grad_ok stays false and the gradient runs per summand.)
+    // (else: the product table is too large for the GEMM-regime kernel: values run the block-sparse kernel, one output per pass)
     if (!sparse_ok) {
         if (!dev.has_dense)
             return fail(SMX_ERR_UNSUPPORTED, plan.has_sparse ? "plan has a cold block that is not a contiguous tile of x"
@@ -196,19 +188,13 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         }
     }
     if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
-    dev.n_sets = plan.n_sets;
-    dev.n_gd = (int32_t)plan.grad_dims.size();
-    dev.grad_ok = !dev.deep && (dev.has_dense_grad || (plan.n_sets == plan.d_out * (1 + (int64_t)plan.grad_dims.size()) &&
-                                         (dev.n_gd > 0 || plan.hot_dims == 0 || plan.n_hot == 0)));
-    if ((rc = upload(plan.grad_dims, &dev.grad_dims, dev.bytes))) return rc;
     dev.has_sparse = true;
     return SMX_OK;
 }
 
 void fast_free(FastDevice& d) {
     void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.pipe_dir, d.chunk_meta, d.coef, d.c0,
-                    d.grad_dims, d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef,
-                    d.dense_grad_coef, d.dense_grad_c0, d.dense_grad_col};
+                    d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -230,18 +216,25 @@ __global__ void nan_at_nodes_kernel(const double* __restrict__ x, long long N, l
     }
 }
 
-int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, int gradient, cudaStream_t st) {
-    // TMA needs 16-byte aligned rows.  Anything else (odd pitch, odd base address) is first packed into an aligned
-    // scratch copy on the same stream; callers that care about the last few percent pass aligned rows.
-    double* scratch = nullptr;
+// TMA needs 16-byte aligned rows.  Anything else (odd pitch, odd base address) is first packed into an aligned scratch copy
+// on the same stream; callers that care about the last few percent pass aligned rows.  *scratch is freed by the caller.
+int aligned_rows(int64_t d_in, const double*& x, int64_t N, int64_t& ldx, double** scratch, cudaStream_t st) {
+    *scratch = nullptr;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (ldx & 1) != 0) {
-        const int64_t pitch = (d.d_in + 1) & ~(int64_t)1;
-        SMX_CUDA(cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)N * pitch, st));
-        SMX_CUDA(cudaMemcpy2DAsync(scratch, sizeof(double) * pitch, x, sizeof(double) * ldx, sizeof(double) * d.d_in, (size_t)N,
+        const int64_t pitch = (d_in + 1) & ~(int64_t)1;
+        SMX_CUDA(cudaMallocAsync((void**)scratch, sizeof(double) * (size_t)N * pitch, st));
+        SMX_CUDA(cudaMemcpy2DAsync(*scratch, sizeof(double) * pitch, x, sizeof(double) * ldx, sizeof(double) * d_in, (size_t)N,
                                    cudaMemcpyDeviceToDevice, st));
-        x = scratch;
+        x = *scratch;
         ldx = pitch;
     }
+    return SMX_OK;
+}
+
+int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, cudaStream_t st) {
+    double* scratch = nullptr;
+    int rca = aligned_rows(d.d_in, x, N, ldx, &scratch, st);
+    if (rca) return rca;
     FastArgs a;
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
@@ -256,9 +249,7 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.ldx = ldx;
     a.d_out = d.d_out;
     a.num_tiles = (N + kTile - 1) / kTile;
-    a.gradient = gradient;
-    a.n_gd = d.has_dense_grad ? 0 : d.n_gd;  // dense derivative columns: this kernel only runs the function's own sets
-    a.grad_dims = d.grad_dims;
+    a.gradient = 0;
     a.d_in = d.d_in;
     a.n_hot = d.n_hot;
     a.n_hot_rows = d.n_hot_rows;
@@ -283,12 +274,12 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
 int fast_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
     if (N == 0) return SMX_OK;
     if (!d.has_sparse) return fail(SMX_ERR_UNSUPPORTED, "plan has no block-sparse form");
-    return run_fast(d, x, N, ldx, y, 0, st);
+    return run_fast(d, x, N, ldx, y, st);
 }
 
 namespace {
 
-int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, bool gradient, cudaStream_t st) {
+int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* out, cudaStream_t st) {
     DenseArgs a;
     a.eta = d.eta;
     a.tab_pairs = reinterpret_cast<const int2*>(d.tab_pairs);
@@ -296,13 +287,13 @@ int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.hot_pos = d.hot_pos;
     a.meta = reinterpret_cast<const int2*>(d.dense_meta);
     a.eta0 = d.dense_eta0;
-    a.coef = gradient ? d.dense_grad_coef : d.dense_coef;
-    a.c0 = gradient ? d.dense_grad_c0 : d.c0;
-    a.colmap = gradient ? d.dense_grad_col : nullptr;
+    a.coef = d.dense_coef;
+    a.c0 = d.c0;
+    a.colmap = nullptr;
     a.N = N;
     a.ldx = ldx;
-    a.ncol = gradient ? d.d_out * d.n_gd : d.d_out;
-    a.ldy = gradient ? d.d_out * d.d_in : d.d_out;
+    a.ncol = d.d_out;
+    a.ldy = d.d_out;
     a.k4 = d.dense_k4;
     a.nblk = (int)((a.ncol + 7) / 8);
     a.n_tab = d.n_tab;
@@ -319,26 +310,124 @@ int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
 int dense_eval(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* y, cudaStream_t st) {
     if (N == 0) return SMX_OK;
     if (!d.has_dense) return fail(SMX_ERR_UNSUPPORTED, "plan has no dense form");
-    return run_dense(d, x, N, ldx, y, false, st);
+    return run_dense(d, x, N, ldx, y, st);
 }
 
-int fast_gradient(const FastDevice& d, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st) {
+int fast_gradient(const FastDevice& d, const GradDevice& g, const double* x, int64_t N, int64_t ldx, double* J, bool nan_at_nodes, cudaStream_t st) {
     if (N == 0) return SMX_OK;
-    if (!d.has_sparse || !d.grad_ok) return fail(SMX_ERR_UNSUPPORTED, "plan has no derivative sets");
-    // dimensions without any entry keep derivative zero; everything else is written by the kernel
-    SMX_CUDA(cudaMemsetAsync(J, 0, sizeof(double) * (size_t)N * d.d_out * d.d_in, st));
-    // block-sparse kernel: derivatives w.r.t. the cold columns (row sums) and, unless they are dense columns, the
-    // derivative sets of the hot dimensions; dense kernel: the derivative sets as columns of Phi G
-    int rc = SMX_OK;
-    if ((!d.has_dense_grad || d.has_cold) && (rc = run_fast(d, x, N, ldx, J, 1, st))) return rc;
-    if (d.has_dense_grad && (rc = run_dense(d, x, N, ldx, J, true, st))) return rc;
-    if (nan_at_nodes) {
-        const long long total = (long long)N * d.d_in;
-        const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)d.sm_count * 16);
-        nan_at_nodes_kernel<<<blocks, 256, 0, st>>>(x, N, ldx, d.d_in, d.d_out, d.nan_off, d.nan_nodes, J);
-        SMX_LAUNCH_CHECK("nan_at_nodes_kernel");
+    if (!g.present) return fail(SMX_ERR_UNSUPPORTED, "plan has no gradient jobs");
+    double* scratch = nullptr;
+    int rc = aligned_rows(d.d_in, x, N, ldx, &scratch, st);
+    if (rc) return rc;
+    rc = grad_kernel_launch(d, g, x, N, ldx, J, nan_at_nodes, st);  // writes every entry of J exactly once
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// Gradient jobs of the plan -> device: records (metadata + coefficients packed as DMMA B fragments, one per item and output),
+// the jobs assigned to the warps of a CTA by longest processing time, the directory in the order the warps walk it.
+int grad_upload(const FastPlan& plan, const FastDevice& dev, GradDevice& g) {
+    g = GradDevice();
+    const GradPlan& G = plan.grad;
+    if (!G.present || !plan.flat_ok || !dev.has_sparse) return SMX_OK;  // (no gradient kernel for eight-factor records yet)
+    const int32_t n_items = (int32_t)G.item_off.size() - 1, n_jobs = (int32_t)G.job_kind.size();
+    const size_t dout = (size_t)plan.d_out;
+    g.n_items = n_items, g.n_jobs = n_jobs, g.n_zero = (int32_t)G.zero_cols.size() / 2;
+    int device = 0, smem_sm = 0;
+    SMX_CUDA(cudaGetDevice(&device));
+    SMX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    g.warps = grad_kernel_warps(g, dev, smem_sm);
+    if (g.warps == 0) return SMX_OK;
+    // records
+    std::vector<int32_t> rec_off((size_t)n_items), units((size_t)n_items);
+    size_t total = 0;
+    for (int32_t it = 0; it < n_items; ++it) {
+        const size_t ks = (size_t)((G.item_off[it + 1] - G.item_off[it] + 3) / 4);
+        rec_off[it] = (int32_t)total, units[it] = (int32_t)(5 + 4 * ks);
+        total += dout * (5 + 4 * ks);
+        if (total >= (size_t)INT32_MAX) return SMX_OK;  // too many outputs for one set of gradient tables: the host layer splits them
     }
+    std::vector<double> records(total * 16, 0.0);
+    std::vector<int32_t> meta(kMetaInts);
+    for (int32_t it = 0; it < n_items; ++it) {
+        const size_t r0 = (size_t)G.item_off[it], rows = (size_t)G.item_off[it + 1] - r0, ks = (rows + 3) / 4;
+        std::copy_n(&G.item_meta[(size_t)it * kMetaInts], kMetaInts, meta.begin());
+        for (int i = 0; i < 16; ++i) meta[i] *= kTabPitch, meta[48 + i] *= kTabPitch;
+        for (int i = 96; i < 160; ++i) meta[i] *= kTabPitch;
+        for (size_t o = 0; o < dout; ++o) {
+            double* rec = &records[((size_t)rec_off[it] + o * units[it]) * 16];
+            std::memcpy(rec, meta.data(), kMetaInts * 4);
+            double* packed = rec + 5 * 16;
+            for (size_t s2 = 0; s2 < ks; ++s2)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < 2; ++j) {
+                        const size_t row = 4 * s2 + (lane & 3);
+                        const int gid = lane >> 2, entry = 4 * (gid >> 1) + 2 * j + (gid & 1);
+                        if (row < rows) packed[s2 * kKStepDoubles + 2 * lane + j] = G.coef[((r0 + row) * dout + o) * kBlockWidth + entry];
+                    }
+        }
+    }
+    int rc;
+    if ((rc = upload(records, &g.records, g.bytes, 2))) return rc;
+    std::vector<double>().swap(records);
+    // jobs -> warps (longest processing time first); cost of an item as in the value path
+    auto item_cost = [&](int32_t it) { return 2.0 + (double)((G.item_off[it + 1] - G.item_off[it] + 3) / 4); };
+    std::vector<double> job_cost((size_t)n_jobs, 0.0);
+    for (int32_t jb = 0; jb < n_jobs; ++jb)
+        for (int32_t it = G.job_off[jb]; it < G.job_off[jb + 1]; ++it) job_cost[jb] += item_cost(it);
+    std::vector<int32_t> by_cost((size_t)n_jobs);
+    for (int32_t jb = 0; jb < n_jobs; ++jb) by_cost[jb] = jb;
+    std::stable_sort(by_cost.begin(), by_cost.end(), [&](int32_t a1, int32_t a2) { return job_cost[a1] > job_cost[a2]; });
+    std::vector<std::vector<int32_t>> lists((size_t)g.warps);
+    std::vector<double> load((size_t)g.warps, 0.0);
+    for (int32_t jb : by_cost) {
+        const size_t w = std::min_element(load.begin(), load.end()) - load.begin();
+        lists[w].push_back(jb);
+        load[w] += job_cost[jb];
+    }
+    std::vector<int32_t> dir((size_t)n_items * 4), jobs((size_t)n_jobs * 4, 0);
+    size_t pos = 0;
+    int32_t cold_ordinal = 0;
+    std::vector<int32_t> node_off((size_t)n_jobs, 0);
+    for (int32_t jb = 0; jb < n_jobs; ++jb)
+        if (G.job_kind[jb] == 0) node_off[jb] = 32 * cold_ordinal++;
+    for (int w = 0; w < g.warps; ++w) {
+        g.warp_off[w] = (int32_t)pos;
+        for (int32_t jb : lists[w]) {
+            const bool cold_job = G.job_kind[jb] == 0;
+            for (int32_t it = G.job_off[jb]; it < G.job_off[jb + 1]; ++it) {
+                const int32_t* d4 = &G.item_dir[(size_t)it * 4];
+                const int32_t ks = (d4[1] + 3) / 4, nf = (d4[2] >> 8) & 15;
+                const bool hot = d4[2] & kChunkHot, first = it == G.job_off[jb], last = it + 1 == G.job_off[jb + 1];
+                int32_t flags = (hot ? 1 : 0) | (first ? 4 : 0) | (last ? 8 : 0) | ((d4[2] & kChunkEtaZero) ? 16 : 0) | (cold_job ? 32 : 0);
+                if (cold_job ? last : !hot) flags |= 2;  // x tile: the cold job's node test; the leading basis values of a cold block
+                dir[pos * 4 + 0] = rec_off[it];
+                dir[pos * 4 + 1] = jb;
+                dir[pos * 4 + 2] = flags | (nf << 8) | (units[it] << 16) | (ks << 24);
+                dir[pos * 4 + 3] = d4[3];
+                if (last && cold_job) jobs[(size_t)jb * 4 + 2] = d4[3];
+                ++pos;
+            }
+            jobs[(size_t)jb * 4 + 0] = G.job_target[jb];
+            jobs[(size_t)jb * 4 + 1] = node_off[jb];
+            jobs[(size_t)jb * 4 + 3] = G.job_kind[jb];
+        }
+    }
+    for (int w = g.warps; w <= kMaxWarps; ++w) g.warp_off[w] = (int32_t)pos;
+    if ((rc = upload(dir, &g.dir, g.bytes, 4))) return rc;
+    if ((rc = upload(jobs, &g.jobs, g.bytes, 4))) return rc;
+    if ((rc = upload(G.job_c0, &g.job_c0, g.bytes))) return rc;
+    if ((rc = upload(G.job_nodes, &g.job_nodes, g.bytes))) return rc;
+    if ((rc = upload(G.zero_cols, &g.zero_cols, g.bytes, 2))) return rc;
+    g.present = true;
     return SMX_OK;
+}
+
+void grad_free(GradDevice& g) {
+    void* ptrs[] = {g.records, g.dir, g.jobs, g.job_c0, g.job_nodes, g.zero_cols};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    g = GradDevice();
 }
 
 }  // namespace smx

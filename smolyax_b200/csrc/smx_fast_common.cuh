@@ -55,6 +55,8 @@ struct alignas(16) ItemBuffer {
 static_assert(offsetof(ItemBuffer, coef) == kMetaInts * 4, "metadata record layout");
 
 int fast_kernel_prepare(FastDevice& d);
+// tensor map of x: (N rows) x (d_in columns) fp64, row pitch ldx * 8 bytes (16-byte aligned rows); box = 16 columns x 32 rows
+int make_x_tensor_map(CUtensorMap* map, const double* x, int64_t d_in, int64_t N, int64_t ldx);
 // few outputs (2 <= d_out < 32): several coefficient sets per pass (smx_fast_multi.cu)
 bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* warps);
 int multi_kernel_launch(const CUtensorMap& map, const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st);

@@ -41,20 +41,18 @@ struct alignas(16) ItemStage {
 };
 
 // One lane of the warp issues the copies of work item c into item buffer `buf` (and, for cold blocks, the x tile).
-template <int ABL = 0>
 __device__ __forceinline__ void stage_item(const FastArgs& a, const CUtensorMap* xmap, ItemStage& st, double* xs, int buf, int c,
                                            const int4 dir, long long o, long long p0) {
     const int ksteps = (dir.y + 3) >> 2;
     const unsigned coef_bytes = (unsigned)ksteps * kKStepDoubles * 8;
-    const bool cold = ABL == 3 ? false : !(dir.z & kChunkHot);
+    const bool cold = !(dir.z & kChunkHot);
     mbar_expect_tx(&st.bar[buf], kMetaInts * 4 + coef_bytes + (cold ? kXTileBytes : 0));
     // metadata + coefficients of (item, set o) are one contiguous record: a single bulk copy
     bulk_copy(&st.item[buf], a.coef + ((size_t)dir.x + (size_t)o * (5 + 4 * ksteps)) * 16, kMetaInts * 4 + coef_bytes, &st.bar[buf]);
     if (cold) tma_load_2d(xs, xmap, dir.w, (int)p0, &st.bar[buf]);
 }
 
-// ABL != 0 are timing experiments (wrong results on purpose): 1 = no DMMA, 2 = no prologue, 3 = no x tiles / basis values
-template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2, bool FLAT = false>
+template <int NW, int CTAS, int EARLY = 2, bool FLAT = false>
 __global__ void __launch_bounds__(NW * 32, CTAS)
 fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, const double* __restrict__ x, double* __restrict__ y) {
     constexpr int kThreads = NW * 32;
@@ -113,7 +111,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
         // ---- prologue: value table = 1 | 1-D basis values of the hot entries | products of hot pairs, level by level ----
         if (tid < kTile) tab[tid] = 1.0;
-        if (ABL != 2) {
+        {
             const int slot = t_slot(lane);
             auto hot_dim = [&](int d, double xv) {
                 double v = 1.0;
@@ -131,7 +129,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
             }
         }
         __syncthreads();
-        if (ABL != 2 && !FLAT) {
+        if (!FLAT) {
             // products of 2..4 hot pairs in one pass straight from the hot rows (row 0 = 1 pads short products) ..
             // (two points per thread: rows are 16-byte aligned and the products are elementwise)
             const int flat_begin = 1 + a.n_hot_rows, count = a.n_flat * (kTile / 2);
@@ -160,20 +158,12 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);  // lands during the main loop
 
         // ---- main: block-sparse contraction, one coefficient set at a time ------------------------------------------------
-        // values: set = output.  gradient: per output, the function's own set (whose cold-block row sums are the
-        // derivatives w.r.t. the cold columns) followed by one derivative set per hot dimension.
-        const int n_pass = GRAD ? (int)a.d_out * (1 + a.n_gd) : (int)a.d_out;
+        const int n_pass = (int)a.d_out;
         for (int pass = 0; pass < n_pass; ++pass) {
-            long long o = pass, set = pass;
-            int gq = 0;
-            if (GRAD) {
-                o = pass / (1 + a.n_gd);
-                gq = pass - (int)o * (1 + a.n_gd);
-                set = gq == 0 ? o : a.d_out + o * a.n_gd + (gq - 1);
-            }
+            const long long o = pass, set = pass;
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             const int c_begin = a.warp_off[warp], c_end = a.warp_off[warp + 1];
-            if (c_begin < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], set, p0);
+            if (c_begin < c_end && lane == 0) stage_item(a, &xmap, st, xs, k_item & 1, c_begin, s_dir[c_begin], set, p0);
             for (int c = c_begin; c < c_end; ++c, ++k_item) {
                 const int buf = k_item & 1;
                 const int4 dir = s_dir[c];
@@ -216,7 +206,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
 
                 // leading basis values pi_e(x_p) of the lane's 4 points x 4 entries (entries 4 tig .. 4 tig + 3)
                 double v[4][4];
-                if (ABL == 3 || (dir.z & kChunkHot)) {
+                if (dir.z & kChunkHot) {
                     const int4 t4 = *reinterpret_cast<const int4*>(ib.tab + 4 * tig);
                     const int tabs[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
@@ -239,7 +229,7 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
-                if (c + 1 < c_end && lane == 0) stage_item<ABL>(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], set, p0);
+                if (c + 1 < c_end && lane == 0) stage_item(a, &xmap, st, xs, buf ^ 1, c + 1, s_dir[c + 1], set, p0);
 
                 // acc[i][j] (8 x 8 tiles) = sum over k-steps of A (value-table rows) * B (packed coefficients).
                 // Every k-step runs both n-tiles: after the degree-major ordering of the hot entries all but one or two of
@@ -250,8 +240,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const double af[4] = {a0lo.x, a0lo.y, a0hi.x, a0hi.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        dmma_first<ABL>(acc[i][0], af[i], b0.x);
-                        dmma_first<ABL>(acc[i][1], af[i], b0.y);
+                        dmma_first<0>(acc[i][0], af[i], b0.x);
+                        dmma_first<0>(acc[i][1], af[i], b0.y);
                     }
                 }
                 if (ksteps > 1) {
@@ -262,8 +252,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                     const double af[4] = {a1lo.x, a1lo.y, a1hi.x, a1hi.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        dmma_<ABL>(acc[i][0], af[i], b1.x);
-                        dmma_<ABL>(acc[i][1], af[i], b1.y);
+                        dmma_<0>(acc[i][0], af[i], b1.x);
+                        dmma_<0>(acc[i][1], af[i], b1.y);
                     }
                 }
                 if (ksteps > 2) {
@@ -277,28 +267,8 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                         const double af[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            dmma_<ABL>(acc[i][0], af[i], b.x);
-                            dmma_<ABL>(acc[i][1], af[i], b.y);
-                        }
-                    }
-                }
-                if (GRAD && gq == 0 && !(dir.z & kChunkHot)) {
-                    // d I_o / d x_j for the block's columns j: pi_e = x_j - eta_0, so the derivative is the row sum itself
-                    const int4 dg = *reinterpret_cast<const int4*>(ib.deg + 4 * tig);
-                    const bool split = dir.z & kChunkSplit;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const long long p = p0 + gid + 8 * i;
-                        if (p < a.N) {
-                            double* jr = y + (p * a.d_out + o) * a.d_in + dir.w + 4 * tig;
-                            const double g4[4] = {acc[i][0][0], acc[i][0][1], acc[i][1][0], acc[i][1][1]};
-                            const int d4[4] = {dg.x, dg.y, dg.z, dg.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                if (d4[e] == 0) continue;      // dummy entry: its column belongs to someone else
-                                if (split) atomicAdd(jr + e, g4[e]);  // at most a few items per block; J starts at zero
-                                else jr[e] = g4[e];
-                            }
+                            dmma_<0>(acc[i][0], af[i], b.x);
+                            dmma_<0>(acc[i][1], af[i], b.y);
                         }
                     }
                 }
@@ -321,12 +291,11 @@ fast_eval_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                 for (int i = 0; i < 4; ++i) xs[gid + 8 * i] = tot[i];  // the warp's x buffer is idle now: reuse it for its partial sums
             }
             __syncthreads();
-            if (tid < kTile && p0 + tid < a.N && !(GRAD && gq == 0)) {
+            if (tid < kTile && p0 + tid < a.N) {
                 double s = __ldg(a.c0 + set);
 #pragma unroll
                 for (int w = 0; w < NW; ++w) s += xtiles[w].v[tid];
-                if (GRAD) y[((p0 + tid) * a.d_out + o) * a.d_in + __ldg(a.grad_dims + gq - 1)] = s;
-                else y[(p0 + tid) * a.d_out + o] = s;
+                y[(p0 + tid) * a.d_out + o] = s;
             }
             // the x buffers are rewritten (by TMA) only after the barriers of the next prologue, the value table only by that
             // prologue (every warp is past the barrier above): the last output of a tile needs no second barrier
@@ -644,12 +613,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int NW, int CTAS, int ABL = 0, bool GRAD = false, int EARLY = 2, bool FLAT = false>
+template <int NW, int CTAS, int EARLY = 2, bool FLAT = false>
 int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count * CTAS);
-    if (ABL != 0 || GRAD || EARLY != 2 || FLAT)
-        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, FLAT)));
-    fast_eval_kernel<NW, CTAS, ABL, GRAD, EARLY, FLAT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, FLAT), st>>>(map, a, x, y);
+    if (EARLY != 2 || FLAT)
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, EARLY, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, FLAT)));
+    fast_eval_kernel<NW, CTAS, EARLY, FLAT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, FLAT), st>>>(map, a, x, y);
     SMX_LAUNCH_CHECK("fast_eval_kernel");
     return SMX_OK;
 }
@@ -671,12 +640,10 @@ int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
 }
 template <int NW>
 int launch_lean(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
+    // (staging by an elected lane: measured 1.847 vs 1.888 ms against lane 0; single-output instantiation: 1.805 vs 1.818)
     if (d.deep) return d.eta0_zero ? launch_lean2<NW, true, false, true, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, true>(map, a, d, x, y, st);
-    static const int one = tune_int("SMX_FAST_ONE", 1);  // tuning knob
-    if (one && a.d_out == 1) return d.eta0_zero ? launch_lean2<NW, true, false, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false, true>(map, a, d, x, y, st);
-    static const int elect = tune_int("SMX_FAST_ELECT", 1);  // tuning knob (measured: 1.847 vs 1.888 ms)
-    if (elect) return d.eta0_zero ? launch_lean2<NW, true, false, true, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false>(map, a, d, x, y, st);
-    return d.eta0_zero ? launch_lean2<NW, true, false, false, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, false, false>(map, a, d, x, y, st);
+    if (a.d_out == 1) return d.eta0_zero ? launch_lean2<NW, true, false, true, false, true>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false, true>(map, a, d, x, y, st);
+    return d.eta0_zero ? launch_lean2<NW, true, false, true, false>(map, a, d, x, y, st) : launch_lean2<NW, false, false, true, false>(map, a, d, x, y, st);
 }
 
 }  // namespace
@@ -720,9 +687,9 @@ static int prepare_shape(FastDevice& d) {
             return SMX_OK;
         }
     }
-    if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 7 || want == 6)) {
-        for (int nw : {8, 7, 6}) {
-            if (want != nw && (want != 0 || nw == 7)) continue;  // (7 only on request)
+    if (d.flat_ok && want_flat && (want == 0 || want == 8 || want == 6)) {
+        for (int nw : {8, 6}) {
+            if (want != nw && want != 0) continue;
             if (2 * (smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) {
                 d.flat = true;
                 d.warps = nw;
@@ -763,50 +730,44 @@ static int prepare_shape(FastDevice& d) {
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 12)));
     if (d.warps == 16) {
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
-        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1, 0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
+        SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, 16)));
     }
     return SMX_OK;
 }
 
-int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st) {
-    // tensor map of x: (N rows) x (d_in columns) fp64, row pitch ldx * 8 bytes; box = 16 columns x 32 rows
-    CUtensorMap map;
-    const cuuint64_t dims[2] = {(cuuint64_t)d.d_in, (cuuint64_t)a.N};
-    const cuuint64_t strides[1] = {(cuuint64_t)a.ldx * sizeof(double)};
+int make_x_tensor_map(CUtensorMap* map, const double* x, int64_t d_in, int64_t N, int64_t ldx) {
+    if (encode_tiled() == nullptr) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)d_in, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(double)};
     const cuuint32_t box[2] = {kBlockWidth, kTile};
     const cuuint32_t estr[2] = {1, 1};
     // L2 promotion: a tile row is 128 bytes; with 256-byte promotion the fetch also brings the same rows of the next column
     // block into L2 (another item of the same tile, a few microseconds later)
     static const int promo = tune_int("SMX_FAST_L2PROMO", 256);  // (measured: 1.790 vs 1.799 ms)
-    const CUresult res = encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
+    const CUresult res = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                         promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                         : promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)res));
-    if (d.pipe_warps > 0 && !a.gradient && a.N < (1ll << 31) - kTile) return pipe_kernel_launch(map, d, a, x, y, st);
-    if (d.multi && !a.gradient) return multi_kernel_launch(map, d, a, x, y, st);
+    return SMX_OK;
+}
+
+int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, double* y, cudaStream_t st) {
+    CUtensorMap map;
+    const int rc_map = make_x_tensor_map(&map, x, d.d_in, a.N, a.ldx);
+    if (rc_map) return rc_map;
+    if (d.pipe_warps > 0 && a.N < (1ll << 31) - kTile) return pipe_kernel_launch(map, d, a, x, y, st);
+    if (d.multi) return multi_kernel_launch(map, d, a, x, y, st);
     if (d.flat) {
-        if (a.gradient && d.deep) return fail(SMX_ERR_UNSUPPORTED, "eight-factor records: the fast path has no gradient kernel for them");
-        if (a.gradient && d.warps == 7) return fail(SMX_ERR_UNSUPPORTED, "7 warps per CTA: lean kernel only (tuning knob)");
-        if (a.gradient && d.warps == 12) return launch<12, 1, 0, true, 2, true>(map, a, d, x, y, st);
-        if (a.gradient) return d.warps == 8 ? launch<8, 2, 0, true, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, true, 2, true>(map, a, d, x, y, st);
-        // values: the lean item loop (SMX_FAST_LEAN=0 selects the general kernel, for A/B timing)
+        // the lean item loop (SMX_FAST_LEAN=0 in a tuning build selects the general kernel, for A/B timing)
         static const int lean = tune_int("SMX_FAST_LEAN", 1);
         if (d.deep && a.N >= (1ll << 31) - kTile) return fail(SMX_ERR_UNSUPPORTED, "more than 2^31 points in one call");
         if ((lean || d.deep) && a.N < (1ll << 31) - kTile) {
             if (d.warps == 8) return launch_lean<8>(map, a, d, x, y, st);
-            if (d.warps == 7) return launch_lean<7>(map, a, d, x, y, st);
             if (d.warps == 6) return launch_lean<6>(map, a, d, x, y, st);
         }
-        if (d.warps == 7) return fail(SMX_ERR_UNSUPPORTED, "7 warps per CTA: lean kernel only (tuning knob)");
-        return d.warps == 8 ? launch<8, 2, 0, false, 2, true>(map, a, d, x, y, st) : launch<6, 2, 0, false, 2, true>(map, a, d, x, y, st);
-    }
-    if (a.gradient) {
-        if (d.warps == 4) return launch<4, 2, 0, true>(map, a, d, x, y, st);
-        if (d.warps == 8) return launch<8, 1, 0, true>(map, a, d, x, y, st);
-        if (d.warps == 16) return launch<16, 1, 0, true>(map, a, d, x, y, st);
-        return launch<12, 1, 0, true>(map, a, d, x, y, st);
+        return d.warps == 8 ? launch<8, 2, 2, true>(map, a, d, x, y, st) : launch<6, 2, 2, true>(map, a, d, x, y, st);
     }
     if (d.warps == 4) return launch<4, 2>(map, a, d, x, y, st);
     if (d.warps == 8) return launch<8, 1>(map, a, d, x, y, st);
@@ -814,7 +775,7 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
         // 16 warps leave 128 registers per thread: pre-loading one k-step (not two) keeps the kernel spill free (measured)
         static const int early = tune_int("SMX_FAST_EARLY", 1);
         if (early == 2) return launch<16, 1>(map, a, d, x, y, st);
-        return launch<16, 1, 0, false, 1>(map, a, d, x, y, st);
+        return launch<16, 1, 1>(map, a, d, x, y, st);
     }
     return launch<12, 1>(map, a, d, x, y, st);
 }

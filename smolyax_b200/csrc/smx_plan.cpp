@@ -562,67 +562,65 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     for (size_t e = 0; e < plan.ent_dim.size(); ++e)
         if (plan.ent_tab[e] > 0) hot_tab[(int64_t)plan.ent_dim[e] * kCode + plan.ent_deg[e]] = plan.ent_tab[e];
 
-    // ---- 7b. gradient coefficient sets ---------------------------------------------------------------------------------
+    // ---- 7b. derivative coefficients, sparse --------------------------------------------------------------------------
     // d/dx_i of the interpolant is a polynomial over the same term set: a term with the pair (i, b) contributes to the
-    // terms with (i, k), k < b, through  pi_b' = sum_k D[b][k] pi_k  (D from pi_b = pi_{b-1} (x - eta_{b-1})).
-    // One set per output and hot dimension with an entry; cold dimensions need none (pi = x - eta_0, pi' = 1).
-    std::vector<std::vector<ld>> Cd;  // [grad dim][T * d_out]
+    // terms with (i, k), k < b, through  pi_b' = sum_k D[b][k] pi_k  (D from pi_b = pi_{b-1} (x - eta_{b-1})).  Only hot
+    // dimensions need it (cold ones: pi = x - eta_0, pi' = 1, the derivative is a row sum of the value contraction), and
+    // only the terms that contain the dimension carry a coefficient: Cd[h] maps term -> d_out coefficients.
+    std::vector<std::unordered_map<int32_t, std::vector<ld>>> Cd;
     if (with_gradient) {
         for (int64_t d = 0; d <= hot_dim_max; ++d)
             if (maxdeg[d] > 0) plan.grad_dims.push_back((int32_t)d);
-        const double bytes = (double)plan.grad_dims.size() * (double)T * (double)d_out * sizeof(ld);
-        if (bytes > 3.0e9) plan.grad_dims.clear();  // huge d_out: the gradient stays on the per-summand kernels
-        Cd.assign(plan.grad_dims.size(), std::vector<ld>());
+        // (memory of the sparse sets: terms that contain the dimension x degree x outputs; refuse beyond ~3 GB - the host
+        //  layer then differentiates by blocks of output columns)
+        double cells = 0.0;
+        for (int32_t t = 1; t < T; ++t)
+            for (int64_t code : term_key[t])
+                if (code / kCode <= hot_dim_max) cells += (double)(code % kCode);
+        if (cells * (double)d_out * (sizeof(ld) + 24.0) > 3.0e9) plan.grad_dims.clear();
+        Cd.assign(plan.grad_dims.size(), {});
+        std::vector<int32_t> h_of_dim((size_t)d_in, -1);
+        for (size_t h = 0; h < plan.grad_dims.size(); ++h) h_of_dim[plan.grad_dims[h]] = (int32_t)h;
+        std::vector<std::vector<std::vector<ld>>> Dm((size_t)hot_dim_max + 2);  // per hot dimension: D[b][k]
         for (size_t h = 0; h < plan.grad_dims.size(); ++h) {
             const int d = plan.grad_dims[h], D = maxdeg[d];
             const double* eta = plan.eta.data() + eta_off[d];
-            // Dm[b][k], b = 0..D, k = 0..D-1
-            std::vector<std::vector<ld>> Dm((size_t)D + 1, std::vector<ld>((size_t)D + 1, 0.0L));
+            auto& M = Dm[(size_t)d];
+            M.assign((size_t)D + 1, std::vector<ld>((size_t)D + 1, 0.0L));
             for (int b = 1; b <= D; ++b) {
                 for (int k = 0; k < b - 1; ++k) {
-                    Dm[b][k + 1] += Dm[b - 1][k];
-                    Dm[b][k] += Dm[b - 1][k] * ((ld)eta[k] - (ld)eta[b - 1]);
+                    M[b][k + 1] += M[b - 1][k];
+                    M[b][k] += M[b - 1][k] * ((ld)eta[k] - (ld)eta[b - 1]);
                 }
-                Dm[b][b - 1] += 1.0L;
+                M[b][b - 1] += 1.0L;
             }
-            std::vector<ld>& out = Cd[h];
-            out.assign((size_t)T * d_out, 0.0L);
-            Key key2;
-            for (int32_t t = 1; t < T; ++t) {
-                const Key& key = term_key[t];
-                size_t pos = key.size();
-                for (size_t i = 0; i < key.size(); ++i)
-                    if (key[i] / kCode == d) pos = i;
-                if (pos == key.size()) continue;
-                const int b = (int)(key[pos] % kCode);
+        }
+        Key key2;
+        for (int32_t t = 1; t < T && !plan.grad_dims.empty(); ++t) {
+            const Key& key = term_key[t];
+            const ld* src = &C[(size_t)t * d_out];
+            for (size_t pos = 0; pos < key.size(); ++pos) {
+                const int d = (int)(key[pos] / kCode), b = (int)(key[pos] % kCode);
+                if (d > hot_dim_max) continue;
+                const int32_t h = h_of_dim[d];
                 for (int k = 0; k < b; ++k) {
-                    const ld w = Dm[b][k];
+                    const ld w = Dm[(size_t)d][b][k];
                     if (w == 0.0L) continue;
                     key2 = key;
                     if (k == 0) key2.erase(key2.begin() + pos);
                     else key2[pos] = (int64_t)d * kCode + k;
                     const auto it = term_id.find(key2);
                     if (it == term_id.end()) return "internal error: index set is not downward closed";
-                    const ld* src = &C[(size_t)t * d_out];
-                    ld* dst = &out[(size_t)it->second * d_out];
+                    std::vector<ld>& dst = Cd[(size_t)h][it->second];
+                    if (dst.empty()) dst.assign((size_t)d_out, 0.0L);
                     for (int64_t o = 0; o < d_out; ++o) dst[o] += w * src[o];
                 }
             }
         }
     }
-    const int64_t n_gd = (int64_t)plan.grad_dims.size();
-    // derivative sets as columns of the dense product instead of block-sparse sets: worthwhile from a few dozen columns
-    const bool dense_grad = opt.dense_gradient != 0 && n_gd > 0 && (opt.dense_gradient == 1 || d_out * n_gd >= 32) &&
-                            (double)d_out * (double)n_gd * (double)T * 8.0 <= 3.0e9;
-    plan.n_sets = (int32_t)(d_out * (1 + (dense_grad ? 0 : n_gd)));
-    // coefficient of term t in set s
-    auto coef_of = [&](int32_t t, int64_t set) -> double {
-        if (set < d_out) return (double)C[(size_t)t * d_out + set];
-        const int64_t o = (set - d_out) / n_gd, h = (set - d_out) % n_gd;
-        return (double)Cd[(size_t)h][(size_t)t * d_out + o];
-    };
-    plan.c0.resize((size_t)plan.n_sets);
-    for (int64_t set = 0; set < plan.n_sets; ++set) plan.c0[set] = coef_of(0, set);
+    plan.n_sets = (int32_t)d_out;
+    plan.c0.resize((size_t)d_out);
+    for (int64_t o = 0; o < d_out; ++o) plan.c0[o] = (double)C[(size_t)o];
 
     // ---- 8. value table: level-1 rows alias the hot entries, level >= 2 rows are appended level by level ---------
     const int32_t R = plan.n_rows;
@@ -675,20 +673,23 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     struct Nz {
         int32_t block, row, lane, term;
     };
-    std::vector<Nz> nz;
-    nz.reserve((size_t)T);
-    for (int32_t t = 1; t < T; ++t) {
-        const int64_t lead = term_key[t].back();
-        const int32_t e = ent_index.at(lead);
-        nz.push_back({e / kBlockWidth, row_tab[term_row[t]], e % kBlockWidth, t});
-    }
-    std::sort(nz.begin(), nz.end(), [](const Nz& a, const Nz& b) {
+    auto nz_less = [](const Nz& a, const Nz& b) {
         if (a.block != b.block) return a.block < b.block;
         if (a.row != b.row) return a.row < b.row;
         return a.lane < b.lane;
-    });
+    };
+    std::vector<Nz> nz;
+    nz.reserve((size_t)T);
+    std::vector<Nz> term_nz((size_t)T, Nz{0, 0, 0, 0});  // where term t sits in the (block, row, lane) structure
+    for (int32_t t = 1; t < T; ++t) {
+        const int64_t lead = term_key[t].back();
+        const int32_t e = ent_index.at(lead);
+        term_nz[t] = {e / kBlockWidth, row_tab[term_row[t]], e % kBlockWidth, t};
+        nz.push_back(term_nz[t]);
+    }
+    std::sort(nz.begin(), nz.end(), nz_less);
     // ---- 9a. dense form ------------------------------------------------------------------------------------------------
-    if (opt.dense || dense_grad) {
+    if (opt.dense) {
         const int64_t K = (int64_t)nz.size();
         plan.dense_k4 = (int32_t)(((K + 3) / 4 + kDenseStageK4 - 1) / kDenseStageK4 * kDenseStageK4);
         const int64_t k4s = plan.dense_k4 + kDensePadK4;       // allocated k-steps
@@ -696,7 +697,7 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         plan.dense_eta0.assign((size_t)d_in, 0.0);
         for (int64_t d = 0; d < d_in; ++d)
             if (maxdeg[d] > 0) plan.dense_eta0[d] = plan.eta[eta_off[d]];
-        const int64_t nblk = opt.dense ? (d_out + 7) / 8 : 0;  // (derivative columns only: no value matrix)
+        const int64_t nblk = (d_out + 7) / 8;
         plan.dense_coef.assign((size_t)nblk * k4s * 32, 0.0);
         for (int64_t i = 0; i < K; ++i) {
             const int32_t e = nz[i].block * kBlockWidth + nz[i].lane;
@@ -704,39 +705,15 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             plan.dense_meta[2 * i + 1] = plan.ent_tab[e] > 0 ? plan.ent_tab[e] : -1 - plan.ent_dim[e];
             const int64_t k4 = i >> 2, tig = i & 3;
             const ld* src = &C[(size_t)nz[i].term * d_out];
-            for (int64_t o = 0; o < d_out && opt.dense; ++o)
+            for (int64_t o = 0; o < d_out; ++o)
                 plan.dense_coef[(size_t)(((o >> 3) * k4s + k4) * 32 + 4 * (o & 7) + tig)] = (double)src[o];
         }
-        plan.has_dense = opt.dense;
-        if (dense_grad) {
-            const int64_t ncol = d_out * n_gd, nblk_g = (ncol + 7) / 8;
-            plan.dense_grad_coef.assign((size_t)nblk_g * k4s * 32, 0.0);
-            plan.dense_grad_c0.resize((size_t)ncol);
-            plan.dense_grad_col.resize((size_t)ncol);
-            for (int64_t c = 0; c < ncol; ++c) {
-                const int64_t o = c / n_gd, h = c % n_gd;
-                plan.dense_grad_c0[c] = (double)Cd[(size_t)h][(size_t)o];  // term 0: the constant
-                plan.dense_grad_col[c] = (int32_t)(o * d_in + plan.grad_dims[h]);
-            }
-            for (int64_t i = 0; i < K; ++i) {
-                const int64_t k4 = i >> 2, tig = i & 3;
-                for (int64_t h = 0; h < n_gd; ++h) {
-                    const ld* src = &Cd[(size_t)h][(size_t)nz[i].term * d_out];
-                    for (int64_t o = 0; o < d_out; ++o) {
-                        const int64_t c = o * n_gd + h;
-                        plan.dense_grad_coef[(size_t)(((c >> 3) * k4s + k4) * 32 + 4 * (c & 7) + tig)] = (double)src[o];
-                    }
-                }
-            }
-            plan.has_dense_grad = true;
-        }
+        plan.has_dense = true;
     }
-    if (!opt.sparse) {
-        plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
-        for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
-        if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
-        return finish_nodes();
-    }
+    plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
+    for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
+    if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
+    if (!opt.sparse) return finish_nodes();
     plan.has_sparse = true;
     auto block_flags = [&](int32_t b) {
         int flags = kChunkHot | kChunkContig;
@@ -757,46 +734,51 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         std::vector<int32_t> rows;
         std::vector<double> coef;
     };
+    // (block, row, lane)-sorted non-zeros -> work items of at most kChunkRows rows; coefficient of term t and output o from `coef_fn`
+    auto build_chunks = [&](const std::vector<Nz>& nzl, auto coef_fn, std::vector<Chunk>& chunks) {
+        for (size_t i = 0; i < nzl.size();) {
+            const int32_t b = nzl[i].block;
+            size_t j = i;
+            std::vector<std::pair<int32_t, std::pair<size_t, size_t>>> rows;  // row -> [first, last)
+            while (j < nzl.size() && nzl[j].block == b) {
+                size_t k2 = j;
+                while (k2 < nzl.size() && nzl[k2].block == b && nzl[k2].row == nzl[j].row) ++k2;
+                rows.push_back({nzl[j].row, {j, k2}});
+                j = k2;
+            }
+            const size_t nr = rows.size(), nch = (nr + kChunkRows - 1) / kChunkRows;
+            for (size_t c = 0; c < nch; ++c) {  // split evenly into chunks of at most kChunkRows rows
+                const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
+                Chunk ck;
+                ck.block = b;
+                ck.flags = block_flags(b) | (nch > 1 ? kChunkSplit : 0);
+                ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
+                // order the rows so that every group of four (one DMMA k-step) has four different table-row residues
+                // modulo 4 as long as the item has them: with kTabPitch that makes the A-fragment loads conflict free
+                std::vector<size_t> order;
+                {
+                    std::vector<std::vector<size_t>> cls(4);
+                    for (size_t r = r0; r < r1; ++r) cls[rows[r].first & 3].push_back(r);
+                    size_t taken[4] = {0, 0, 0, 0};
+                    while (order.size() < r1 - r0)
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            if (taken[k4] < cls[k4].size()) order.push_back(cls[k4][taken[k4]++]);
+                }
+                for (size_t pos = 0; pos < order.size(); ++pos) {
+                    const size_t r = order[pos];
+                    ck.rows.push_back(rows[r].first);
+                    for (size_t q = rows[r].second.first; q < rows[r].second.second; ++q)
+                        for (int64_t o = 0; o < d_out; ++o)
+                            ck.coef[(pos * (size_t)d_out + o) * kBlockWidth + nzl[q].lane] = coef_fn(nzl[q].term, o);
+                }
+                chunks.push_back(std::move(ck));
+            }
+            i = j;
+        }
+    };
     std::vector<Chunk> chunks;
-    for (size_t i = 0; i < nz.size();) {
-        const int32_t b = nz[i].block;
-        size_t j = i;
-        std::vector<std::pair<int32_t, std::pair<size_t, size_t>>> rows;  // row -> [first, last)
-        while (j < nz.size() && nz[j].block == b) {
-            size_t k2 = j;
-            while (k2 < nz.size() && nz[k2].block == b && nz[k2].row == nz[j].row) ++k2;
-            rows.push_back({nz[j].row, {j, k2}});
-            j = k2;
-        }
-        const size_t nr = rows.size(), nch = (nr + kChunkRows - 1) / kChunkRows;
-        for (size_t c = 0; c < nch; ++c) {  // split evenly into chunks of at most kChunkRows rows
-            const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
-            Chunk ck;
-            ck.block = b;
-            ck.flags = block_flags(b) | (nch > 1 ? kChunkSplit : 0);
-            ck.coef.assign((r1 - r0) * (size_t)plan.n_sets * kBlockWidth, 0.0);
-            // order the rows so that every group of four (one DMMA k-step) has four different table-row residues
-            // modulo 4 as long as the item has them: with kTabPitch that makes the A-fragment loads conflict free
-            std::vector<size_t> order;
-            {
-                std::vector<std::vector<size_t>> cls(4);
-                for (size_t r = r0; r < r1; ++r) cls[rows[r].first & 3].push_back(r);
-                size_t taken[4] = {0, 0, 0, 0};
-                while (order.size() < r1 - r0)
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        if (taken[k4] < cls[k4].size()) order.push_back(cls[k4][taken[k4]++]);
-            }
-            for (size_t pos = 0; pos < order.size(); ++pos) {
-                const size_t r = order[pos];
-                ck.rows.push_back(rows[r].first);
-                for (size_t q = rows[r].second.first; q < rows[r].second.second; ++q)
-                    for (int64_t set = 0; set < plan.n_sets; ++set)
-                        ck.coef[(pos * (size_t)plan.n_sets + set) * kBlockWidth + nz[q].lane] = coef_of(nz[q].term, set);
-            }
-            chunks.push_back(std::move(ck));
-        }
-        i = j;
-    }
+    build_chunks(nz, [&](int32_t t, int64_t o) { return (double)C[(size_t)t * d_out + o]; }, chunks);
+    const std::vector<Chunk> value_chunks_by_block = chunks;  // (block order: the gradient's cold jobs walk them block by block)
 #ifdef SMX_TUNING
     {   // timing experiments (results are WRONG on purpose; tuning builds only): drop classes of work items to measure what
         // each class costs.  SMX_ABL_DROP bits: 1 = cold items of at most SMX_ABL_THIN_ROWS rows, 2 = other cold items, 4 = hot
@@ -837,35 +819,28 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     }
 
     // ---- 10. kernel-side packing: directory + one contiguous metadata record per work item ------------------------
-    plan.chunk_dir.resize((size_t)plan.n_chunks * 4);
-    plan.chunk_meta.assign((size_t)plan.n_chunks * kMetaInts, 0);
-    plan.chunk_fac2.assign((size_t)plan.n_chunks * 64, 0);
-    plan.chunk_kmask.assign((size_t)plan.n_chunks, 0);
-    plan.padded_fma = 0;
-    for (int32_t c = 0; c < plan.n_chunks; ++c) {
-        const int32_t e0 = plan.chunk_block[c] * kBlockWidth, r0 = plan.chunk_off[c], rows = plan.chunk_off[c + 1] - r0;
+    // item = (entry block `block`, `rows` table rows at rows_ptr, flags) -> dir (4 ints), meta (kMetaInts ints), fac2 (64 ints);
+    // returns the k-mask.  Also records in the plan whether four resp. eight factors per row suffice.
+    const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
+    const int32_t n_flat8 = (int32_t)(plan.tab_factors8.size() / 8);
+    auto pack_item = [&](int32_t block, int32_t flags_in, const int32_t* rows_ptr, int32_t rows, const double* coef, int32_t first_slot,
+                         int32_t* dir, int32_t* meta, int32_t* fac2, int32_t* flags_out) -> int32_t {
+        const int32_t e0 = block * kBlockWidth;
         // which (k-step, half block) pairs carry any coefficient at all (for any output): the others are skipped
         int32_t kmask = 0;
         for (int32_t r = 0; r < rows; ++r)
-            for (int64_t o = 0; o < plan.n_sets; ++o)
+            for (int64_t o = 0; o < d_out; ++o)
                 for (int i = 0; i < kBlockWidth; ++i)
-                    if (plan.coef[((size_t)(r0 + r) * plan.n_sets + o) * kBlockWidth + i] != 0.0) {
+                    if (coef[((size_t)r * d_out + o) * kBlockWidth + i] != 0.0) {
                         // entry i belongs to n-tile j = (i >> 1) & 1 (lane mapping: entry = 4 * (n >> 1) + 2 * j + (n & 1))
                         kmask |= 1 << (2 * (r >> 2) + ((i >> 1) & 1));
                     }
-        plan.chunk_kmask[c] = kmask;
-        plan.padded_fma += 32 * __builtin_popcount((unsigned)kmask);
-        int32_t* dir = &plan.chunk_dir[(size_t)c * 4];
-        int32_t* meta = &plan.chunk_meta[(size_t)c * kMetaInts];
         // every row slot as the product of up to four hot rows (row 0 = the ones row pads): the kernel variant without
         // product rows in the value table multiplies them on the fly.  nf = most factors of any row of the item.
         int32_t nf = 1;
-        const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
-        const int32_t n_flat8 = (int32_t)(plan.tab_factors8.size() / 8);
-        int32_t* fac2 = &plan.chunk_fac2[(size_t)c * 64];
         for (int32_t i = 0; i < kBlockWidth; ++i) {
             int32_t* f4 = meta + 96 + 4 * i;
-            const int32_t row = i < rows ? plan.chunk_rows[r0 + i] : 0;
+            const int32_t row = i < rows ? rows_ptr[i] : 0;
             if (row < flat_begin) {
                 f4[0] = row;
             } else if (row - flat_begin < n_flat) {
@@ -890,24 +865,133 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                 }
             }
         }
-        bool eta_zero = !(plan.chunk_flags[c] & kChunkHot);
+        int32_t flags = flags_in;
+        bool eta_zero = !(flags & kChunkHot);
         for (int i = 0; i < kBlockWidth; ++i) eta_zero = eta_zero && plan.ent_eta0[e0 + i] == 0.0;
-        if (eta_zero) plan.chunk_flags[c] |= kChunkEtaZero;
-        dir[0] = r0, dir[1] = rows, dir[2] = plan.chunk_flags[c] | (nf << 8), dir[3] = plan.ent_dim[e0];
+        if (eta_zero) flags |= kChunkEtaZero;
+        *flags_out = flags;
+        dir[0] = first_slot, dir[1] = rows, dir[2] = flags | (nf << 8), dir[3] = plan.ent_dim[e0];
         double eta0[kBlockWidth];
         for (int i = 0; i < kBlockWidth; ++i) {
             meta[i] = plan.ent_tab[e0 + i];
             meta[16 + i] = plan.ent_deg[e0 + i];
             meta[32 + i] = plan.ent_eta[e0 + i];
             // row indices transposed for the kernel: position 4 * k + s holds row 4 * s + k (k-step s, A-fragment column k)
-            meta[48 + 4 * (i & 3) + (i >> 2)] = i < rows ? plan.chunk_rows[r0 + i] : 0;
+            meta[48 + 4 * (i & 3) + (i >> 2)] = i < rows ? rows_ptr[i] : 0;
             eta0[i] = plan.ent_eta0[e0 + i];
         }
         std::memcpy(meta + 64, eta0, sizeof(eta0));
+        return kmask;
+    };
+    plan.chunk_dir.resize((size_t)plan.n_chunks * 4);
+    plan.chunk_meta.assign((size_t)plan.n_chunks * kMetaInts, 0);
+    plan.chunk_fac2.assign((size_t)plan.n_chunks * 64, 0);
+    plan.chunk_kmask.assign((size_t)plan.n_chunks, 0);
+    plan.padded_fma = 0;
+    for (int32_t c = 0; c < plan.n_chunks; ++c) {
+        const int32_t r0 = plan.chunk_off[c], rows = plan.chunk_off[c + 1] - r0;
+        plan.chunk_kmask[c] = pack_item(plan.chunk_block[c], plan.chunk_flags[c], &plan.chunk_rows[r0], rows,
+                                        &plan.coef[(size_t)r0 * d_out * kBlockWidth], r0, &plan.chunk_dir[(size_t)c * 4],
+                                        &plan.chunk_meta[(size_t)c * kMetaInts], &plan.chunk_fac2[(size_t)c * 64], &plan.chunk_flags[c]);
+        plan.padded_fma += 32 * __builtin_popcount((unsigned)plan.chunk_kmask[c]);
     }
-    plan.hot_off.assign((size_t)plan.hot_dims + 1, 0);
-    for (int32_t d = 0; d < plan.hot_dims; ++d) plan.hot_off[d + 1] = plan.hot_off[d] + maxdeg[d];
-    if (plan.hot_off.back() != plan.n_hot) return "internal error: hot prefix mismatch";
+
+    // ---- 11. gradient: jobs -----------------------------------------------------------------------------------------------
+    // A job produces columns of J for every point of a tile and is run by ONE warp, so nothing is ever added to J:
+    //   kind 0, one per cold block: the row sums acc[p][e] = sum_r C[r][e] m_r(p) of the block's value items ARE dI/dx of
+    //           its 16 columns (pi_e = x - eta_0) - stored straight away (`target` = which of the 16 may be stored: real
+    //           entries, and columns nobody uses; NOT the padding that belongs to a neighbouring block or lies beyond d_in);
+    //   kind 1, one per hot dimension i: the derivative polynomial over the terms that carry a coefficient (section 7b), as
+    //           work items of its own -> one number per point, column `target` = i.
+    // Columns no job writes (dimensions without any entry) are listed in zero_cols and zeroed by the kernel.
+    if (with_gradient && (!plan.grad_dims.empty() || plan.n_hot == 0)) {
+        GradPlan& G = plan.grad;
+        std::vector<char> written((size_t)d_in, 0);
+        auto add_items = [&](const std::vector<Chunk>& cks, size_t begin, size_t end) {
+            for (size_t c = begin; c < end; ++c) {
+                const Chunk& ck = cks[c];
+                const int32_t r0 = (int32_t)G.rows.size();
+                G.rows.insert(G.rows.end(), ck.rows.begin(), ck.rows.end());
+                G.coef.insert(G.coef.end(), ck.coef.begin(), ck.coef.end());
+                G.item_off.push_back((int32_t)G.rows.size());
+                G.item_dir.resize(G.item_dir.size() + 4);
+                G.item_meta.resize(G.item_meta.size() + kMetaInts, 0);
+                std::vector<int32_t> fac2(64, 0);
+                int32_t flags = 0;
+                pack_item(ck.block, ck.flags, ck.rows.data(), (int32_t)ck.rows.size(), ck.coef.data(), r0, &G.item_dir[G.item_dir.size() - 4],
+                          &G.item_meta[G.item_meta.size() - kMetaInts], fac2.data(), &flags);
+            }
+        };
+        G.item_off.push_back(0);
+        G.job_off.push_back(0);
+        for (size_t c = 0; c < value_chunks_by_block.size();) {  // kind 0
+            const int32_t b = value_chunks_by_block[c].block;
+            size_t c1 = c;
+            while (c1 < value_chunks_by_block.size() && value_chunks_by_block[c1].block == b) ++c1;
+            if (!(value_chunks_by_block[c].flags & kChunkHot)) {
+                add_items(value_chunks_by_block, c, c1);
+                const int32_t e0 = b * kBlockWidth, col0 = plan.ent_dim[e0];
+                int32_t mask = 0;
+                for (int i = 0; i < kBlockWidth; ++i) {
+                    const int64_t col = (int64_t)col0 + i;
+                    const bool real = plan.ent_deg[e0 + i] > 0;
+                    // (a padding entry's column is this block's to store only if no entry at all lives there)
+                    if (col < d_in && (real || maxdeg[col] == 0) && !written[col]) mask |= 1 << i, written[col] = 1;
+                }
+                // the two nodes of each column's degree-1 rule: the reference's gradient is NaN there
+                for (int half = 0; half < 2; ++half)
+                    for (int i = 0; i < kBlockWidth; ++i) {
+                        const int64_t col = std::min<int64_t>((int64_t)col0 + i, d_in - 1);
+                        const auto it = pair_id.find({(int)col, 1});
+                        G.job_nodes.push_back(it == pair_id.end() ? std::nan("") : pairs[it->second].nodes[half]);
+                    }
+                G.job_kind.push_back(0);
+                G.job_target.push_back(mask);
+                G.job_off.push_back((int32_t)G.item_off.size() - 1);
+            }
+            c = c1;
+        }
+        for (size_t h = 0; h < plan.grad_dims.size(); ++h) {  // kind 1
+            std::vector<Nz> nzh;
+            for (const auto& kv : Cd[h])
+                if (kv.first != 0) nzh.push_back(term_nz[kv.first]);
+            std::sort(nzh.begin(), nzh.end(), nz_less);
+            std::vector<Chunk> cks;
+            const auto& Ch = Cd[h];
+            build_chunks(nzh, [&](int32_t t, int64_t o) { return (double)Ch.at(t)[(size_t)o]; }, cks);
+            for (Chunk& ck : cks) ck.flags &= ~kChunkSplit;  // (a hot-dimension job adds its items' contributions anyway)
+            add_items(cks, 0, cks.size());
+            G.job_kind.push_back(1);
+            G.job_target.push_back(plan.grad_dims[h]);
+            G.job_off.push_back((int32_t)G.item_off.size() - 1);
+            written[plan.grad_dims[h]] = 1;
+            const auto it0 = Ch.find(0);
+            for (int64_t o = 0; o < d_out; ++o) G.job_c0.push_back(it0 == Ch.end() ? 0.0 : (double)it0->second[(size_t)o]);
+        }
+        // (kind 1 constants are indexed by job: pad the kind 0 jobs' slots)
+        {
+            std::vector<double> c0((size_t)G.job_kind.size() * d_out, 0.0);
+            size_t at = 0;
+            for (size_t jb = 0; jb < G.job_kind.size(); ++jb)
+                if (G.job_kind[jb] == 1) {
+                    std::copy_n(&G.job_c0[at], (size_t)d_out, &c0[jb * d_out]);
+                    at += (size_t)d_out;
+                }
+            G.job_c0.swap(c0);
+        }
+        for (int64_t d = 0; d < d_in;) {  // column ranges nobody writes
+            if (written[d]) {
+                ++d;
+                continue;
+            }
+            int64_t e = d;
+            while (e < d_in && !written[e]) ++e;
+            G.zero_cols.push_back((int32_t)d);
+            G.zero_cols.push_back((int32_t)e);
+            d = e;
+        }
+        G.present = true;
+    }
 
     return finish_nodes();
 }
@@ -974,9 +1058,10 @@ void eval_plan_dense_host(const FastPlan& plan, const double* x, int64_t N, int6
 }
 
 void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, int64_t ldx, double* J) {
-    const int64_t d_out = plan.d_out, d_in = plan.d_in, n_gd = (int64_t)plan.grad_dims.size();
+    // the gradient jobs of the plan, evaluated in fp64 in the order of the kernel (smx_grad_kernel.cu); finite at the nodes
+    const int64_t d_out = plan.d_out, d_in = plan.d_in;
+    const GradPlan& G = plan.grad;
     std::vector<double> tab((size_t)plan.n_tab, 1.0);
-    std::vector<double> tot((size_t)plan.n_sets);
     auto pi = [&](const double* xp, int32_t e) {
         double v = 1.0;
         for (int k = 0; k < plan.ent_deg[e]; ++k) v *= (xp[plan.ent_dim[e]] - plan.eta[plan.ent_eta[e] + k]);
@@ -985,42 +1070,46 @@ void eval_plan_gradient_host(const FastPlan& plan, const double* x, int64_t N, i
     for (int64_t p = 0; p < N; ++p) {
         const double* xp = x + p * ldx;
         double* Jp = J + p * d_out * d_in;
-        std::fill(Jp, Jp + d_out * d_in, 0.0);
+        std::fill(Jp, Jp + d_out * d_in, std::nan(""));  // every entry must be written by exactly one job (or zero_cols)
         for (size_t e = 0; e < plan.ent_dim.size(); ++e)
             if (plan.ent_tab[e] > 0) tab[plan.ent_tab[e]] = pi(xp, (int32_t)e);
         for (int32_t t = 1 + plan.n_hot_rows; t < plan.n_tab; ++t)
             tab[t] = tab[plan.tab_parent[t - 1 - plan.n_hot_rows]] * tab[plan.tab_hot[t - 1 - plan.n_hot_rows]];
-        for (int64_t s = 0; s < plan.n_sets; ++s) tot[s] = plan.c0[s];
-        for (int32_t c = 0; c < plan.n_chunks; ++c) {
-            const int32_t b = plan.chunk_block[c];
-            const bool hot = plan.chunk_flags[c] & kChunkHot;
-            for (int lane = 0; lane < kBlockWidth; ++lane) {
-                const int32_t e = b * kBlockWidth + lane;
-                const double v = hot ? tab[plan.ent_tab[e]] : pi(xp, e);
-                for (int64_t s = 0; s < plan.n_sets; ++s) {
-                    double acc = 0.0;
-                    for (int32_t i = plan.chunk_off[c]; i < plan.chunk_off[c + 1]; ++i)
-                        acc = std::fma(plan.coef[((size_t)i * plan.n_sets + s) * kBlockWidth + lane], tab[plan.chunk_rows[i]], acc);
-                    if (s < d_out && !hot && plan.ent_deg[e] > 0) Jp[s * d_in + plan.ent_dim[e]] += acc;  // cold dim: pi' = 1
-                    tot[s] = std::fma(v, acc, tot[s]);
+        for (size_t z = 0; z + 1 < G.zero_cols.size(); z += 2)
+            for (int64_t o = 0; o < d_out; ++o)
+                for (int32_t c = G.zero_cols[z]; c < G.zero_cols[z + 1]; ++c) Jp[o * d_in + c] = 0.0;
+        for (size_t jb = 0; jb + 1 < G.job_off.size(); ++jb) {
+            for (int64_t o = 0; o < d_out; ++o) {
+                double acc16[kBlockWidth] = {0.0};
+                double tot = G.job_c0[jb * d_out + o];
+                int32_t col0 = 0;
+                for (int32_t it = G.job_off[jb]; it < G.job_off[jb + 1]; ++it) {
+                    const int32_t* dir = &G.item_dir[(size_t)it * 4];
+                    const int32_t* meta = &G.item_meta[(size_t)it * kMetaInts];
+                    const bool hot = dir[2] & kChunkHot;
+                    col0 = dir[3];
+                    for (int lane = 0; lane < kBlockWidth; ++lane) {
+                        double acc = 0.0;
+                        for (int32_t i = G.item_off[it]; i < G.item_off[it + 1]; ++i)
+                            acc = std::fma(G.coef[((size_t)i * d_out + o) * kBlockWidth + lane], tab[G.rows[i]], acc);
+                        if (G.job_kind[jb] == 0) {
+                            acc16[lane] += acc;
+                        } else {
+                            double eta0;
+                            std::memcpy(&eta0, meta + 64 + 2 * lane, sizeof(double));
+                            const double v = hot ? tab[meta[lane]] : (meta[16 + lane] > 0 ? xp[std::min<int64_t>(col0 + lane, d_in - 1)] - eta0 : 1.0);
+                            tot = std::fma(v, acc, tot);
+                        }
+                    }
+                }
+                if (G.job_kind[jb] == 0) {
+                    for (int lane = 0; lane < kBlockWidth; ++lane)
+                        if (G.job_target[jb] >> lane & 1) Jp[o * d_in + col0 + lane] = acc16[lane];
+                } else {
+                    Jp[o * d_in + G.job_target[jb]] = tot;
                 }
             }
         }
-        if (plan.has_dense_grad) {
-            const int64_t k4s = plan.dense_k4 + kDensePadK4;
-            for (int64_t c = 0; c < d_out * n_gd; ++c) {
-                double acc = 0.0;
-                for (int64_t i = 0; i < 4 * (int64_t)plan.dense_k4; ++i) {
-                    const int32_t ia = plan.dense_meta[2 * i], ib = plan.dense_meta[2 * i + 1];
-                    const double phi = tab[ia] * (ib >= 0 ? tab[ib] : xp[-1 - ib] - plan.dense_eta0[-1 - ib]);
-                    acc = std::fma(phi, plan.dense_grad_coef[(size_t)(((c >> 3) * k4s + (i >> 2)) * 32 + 4 * (c & 7) + (i & 3))], acc);
-                }
-                Jp[plan.dense_grad_col[c]] = plan.dense_grad_c0[c] + acc;
-            }
-            continue;
-        }
-        for (int64_t o = 0; o < d_out; ++o)
-            for (int64_t h = 0; h < n_gd; ++h) Jp[o * d_in + plan.grad_dims[h]] = tot[d_out + o * n_gd + h];
     }
 }
 
@@ -1045,11 +1134,10 @@ struct smxh_group {
 static thread_local std::string g_plan_error;
 const char* smxh_plan_error() { return g_plan_error.c_str(); }
 
-// option bits: 1 = derivative sets, 2 = block-sparse form, 4 = dense form, 8 = derivative sets as dense columns
+// option bits: 1 = derivative jobs, 2 = block-sparse form, 4 = dense form
 static smx::PlanOptions plan_options(int32_t bits) {
     smx::PlanOptions o;
     o.gradient = bits & 1, o.sparse = bits & 2, o.dense = bits & 4;
-    o.dense_gradient = (bits & 8) ? 1 : 0;
     return o;
 }
 
@@ -1137,6 +1225,22 @@ void smxh_plan_stats(void* p, int64_t* out) {
     int64_t v[11] = {pl->n_terms, pl->n_entries, pl->n_rows, pl->n_hot, pl->n_chunks, pl->padded_fma,
                      pl->n_levels, pl->nested ? 1 : 0, pl->n_summands, pl->w_raw, pl->w_pad};
     (void)pl->n_tab;
+    std::memcpy(out, v, sizeof(v));
+}
+// gradient jobs: out = [n_jobs, n_items, k-steps of all items, cold jobs, most items of a job, most k-steps of a job, zero ranges]
+void smxh_plan_grad_stats(void* p, int64_t* out) {
+    auto* pl = static_cast<smx::FastPlan*>(p);
+    const smx::GradPlan& G = pl->grad;
+    int64_t ks = 0, cold = 0, maxi = 0, maxk = 0;
+    for (size_t j = 0; j + 1 < G.job_off.size(); ++j) {
+        int64_t k = 0;
+        for (int32_t it = G.job_off[j]; it < G.job_off[j + 1]; ++it) k += (G.item_off[it + 1] - G.item_off[it] + 3) / 4;
+        ks += k;
+        cold += G.job_kind[j] == 0;
+        maxi = std::max<int64_t>(maxi, G.job_off[j + 1] - G.job_off[j]);
+        maxk = std::max(maxk, k);
+    }
+    int64_t v[7] = {(int64_t)G.job_kind.size(), (int64_t)G.item_off.size() - 1, ks, cold, maxi, maxk, (int64_t)G.zero_cols.size() / 2};
     std::memcpy(out, v, sizeof(v));
 }
 // per work item: rows, flags, kmask (statistics for tests and tuning); returns the number of items

@@ -99,6 +99,23 @@ constexpr int kChunkInside = 4;   // .. and the 16 columns all exist (first colu
 constexpr int kChunkSplit = 8;    // the block's rows are spread over more than one item
 constexpr int kChunkEtaZero = 16; // cold block whose first centres are all zero (default Leja domain): pi = x
 
+// Gradient of the fast path (smx_plan.cpp section 11, kernel smx_grad_kernel.cu): jobs, each run by one warp, each writing its
+// own columns of J.  Items are laid out like the value path's (entry block x <= 16 table rows, coefficients [row][output][16]).
+struct GradPlan {
+    bool present = false;
+    std::vector<int32_t> item_off;    // size n_items + 1: row slots of item i are [item_off[i], item_off[i + 1])
+    std::vector<int32_t> rows;        // value-table row of every row slot
+    std::vector<double> coef;         // [row slot][d_out][kBlockWidth]
+    std::vector<int32_t> item_dir;    // 4 ints per item: first row slot, rows, flags | nf << 8, first column of x
+    std::vector<int32_t> item_meta;   // kMetaInts per item (as FastPlan::chunk_meta)
+    std::vector<int32_t> job_off;     // size n_jobs + 1: items of job j
+    std::vector<int32_t> job_kind;    // 0: cold block (row sums = derivatives w.r.t. its 16 columns), 1: hot dimension
+    std::vector<int32_t> job_target;  // kind 0: bit e set = column (first column + e) is stored by this job; kind 1: the dimension
+    std::vector<double> job_c0;       // [job][d_out] constant term of a hot dimension's derivative polynomial (kind 0: zeros)
+    std::vector<double> job_nodes;    // kind 0 jobs, in order: 32 doubles each - node 0 and node 1 of the 16 columns' degree-1 rule
+    std::vector<int32_t> zero_cols;   // pairs [lo, hi): columns of J that no job writes (dimensions without any entry)
+};
+
 struct FastPlan {
     int64_t d_in = 0, d_out = 0;
     bool nested = false;
@@ -135,12 +152,9 @@ struct FastPlan {
     std::vector<int32_t> chunk_flags;
     std::vector<int32_t> chunk_off;      // size n_chunks+1, offsets into chunk_rows / coefficient row slots
     std::vector<int32_t> chunk_rows;     // value-table index of every row slot
-    std::vector<double> coef;            // [row slot][set][kBlockWidth], n_sets coefficient sets per row slot:
-    int32_t n_sets = 0;                  //   set o < d_out: the interpolant's output o;
-    std::vector<int32_t> grad_dims;      //   set d_out + o * grad_dims.size() + h: d/dx_{grad_dims[h]} of output o (same terms,
-                                         //   coefficients mapped through the derivative of the Newton basis); the hot
-                                         //   dimensions with an entry.  Cold dimensions need no set: their derivative is the
-                                         //   row sum acc[p][e] itself (pi_e = x - eta_0).
+    std::vector<double> coef;            // [row slot][output][kBlockWidth]
+    int32_t n_sets = 0;                  // = d_out (coefficient sets per row slot)
+    std::vector<int32_t> grad_dims;      // the hot dimensions with an entry: their derivatives are jobs of kind 1 in `grad`
     // per dimension, the nodes at which the reference's gradient is NaN (barycentric.py:152-154): CSR over dimensions
     std::vector<int32_t> nan_off;
     std::vector<double> nan_nodes;
@@ -161,6 +175,7 @@ struct FastPlan {
     int64_t padded_fma = 0;              // FMAs per point and output the kernel executes: 32 per non-empty (k-step, half block)
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
     bool has_sparse = false;             // work items + coefficient sets above are filled
+    GradPlan grad;                       // derivative jobs (opt.gradient)
     double newton_error = 0.0;           // worst fp64 error of a cardinal function through its Newton form (conditioning check)
 
     // Dense (GEMM-regime) form for large d_out:  y = c0 + Phi(x) C  with one column of Phi per term,
@@ -173,21 +188,12 @@ struct FastPlan {
     std::vector<double> dense_eta0;      // (d_in) first centre of every dimension
     std::vector<double> dense_coef;      // [ceil(d_out / 8)][dense_k4 + kDensePadK4][32]: DMMA B fragments, lane = 4 * gid + tig
                                          // holds C[4 * k4 + tig][8 * jb + gid]
-
-    // Gradient in the dense form: the derivative w.r.t. a hot dimension is a polynomial over the SAME terms with mapped
-    // coefficients, i.e. more columns of the same product:  J[p][o][grad_dims[h]] = gc0[c] + sum_t Phi[p][t] G[t][c],
-    // column c = o * n_gd + h.  (Cold dimensions: row sums of the block-sparse form, as before.)
-    bool has_dense_grad = false;
-    std::vector<double> dense_grad_coef;   // [ceil(d_out n_gd / 8)][dense_k4 + kDensePadK4][32], same packing
-    std::vector<double> dense_grad_c0;     // (d_out n_gd)
-    std::vector<int32_t> dense_grad_col;   // (d_out n_gd) position of column c inside a point's (d_out, d_in) block of J
 };
 
 struct PlanOptions {
-    bool gradient = true;   // derivative coefficient sets (block-sparse sets, or dense columns if `dense` and worthwhile)
+    bool gradient = true;   // derivative jobs (GradPlan; needs the block-sparse form)
     bool sparse = true;     // block-sparse work items (K1; values and gradients)
     bool dense = false;     // dense term matrix (K2; values, large d_out)
-    int dense_gradient = -1;  // derivative sets as dense columns: 1 yes, 0 no, -1 = when there are at least 32 of them
 };
 
 // value-table row (minus one) of hot entry h

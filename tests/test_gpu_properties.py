@@ -307,7 +307,7 @@ def test_out_buffer_of_each_input_kind():
 @pytest.mark.parametrize("mode", ["reference", "compact"])
 def test_tables_from_a_file_give_the_same_bits(tmp_path, mode):
     """``save_layout`` / ``load_layout``: a handle built from the stored tables (no call of ``f``) evaluates and integrates
-    to the same bits as the handle ``set_f`` built, and differentiates to the same numbers."""
+    to the same bits as the handle ``set_f`` built - values, gradient and integral."""
     from smolyax_b200.interpolation import SmolyakBarycentricInterpolator
 
     w = workloads.Workload("file", "leja", 15, 2, 400, 0)
@@ -317,9 +317,8 @@ def test_tables_from_a_file_give_the_same_bits(tmp_path, mode):
     again.load_layout(tmp_path / "tables.npz")
     x = w.points(777, seed=5)
     assert np.array_equal(ip(x), again(x))
-    J, J2 = ip.gradient(x[:50]), again.gradient(x[:50])  # (partial derivatives of split blocks meet in atomics: last bits)
-    assert np.array_equal(np.isnan(J), np.isnan(J2))
-    assert np.max(np.abs(np.nan_to_num(J) - np.nan_to_num(J2))) <= 1e-13 * max(1.0, float(np.nanmax(np.abs(J))))
+    J, J2 = ip.gradient(x[:50]), again.gradient(x[:50])
+    assert np.array_equal(J, J2, equal_nan=True)
     assert np.array_equal(ip.integral(), again.integral())
 
 

@@ -32,7 +32,7 @@ _host.smxh_plan_free.argtypes = [ctypes.c_void_p]
 STATS = ("n_terms", "n_entries", "n_rows", "n_hot", "n_chunks", "padded_fma", "n_levels", "nested", "n_summands", "w_raw", "w_pad")
 
 
-GRADIENT, SPARSE, DENSE, DENSE_GRADIENT = 1, 2, 4, 8  # option bits of smxh_plan_build_opt
+GRADIENT, SPARSE, DENSE = 1, 2, 4  # option bits of smxh_plan_build_opt
 
 
 class _Compact(ctypes.Structure):  # smx_compact_desc
@@ -144,8 +144,10 @@ def test_plan_reproduces_reference_values(case):
 
 @pytest.mark.parametrize("case", ALL_CASES)
 def test_plan_gradient_sets_reproduce_reference_gradients(case):
-    """d/dx_i as extra coefficient sets on the same terms (hot dimensions) + row sums (cold dimensions): equal to the
-    reference's gradient wherever that one is finite, finite at the nodes, and at least as close to the 80-bit referee."""
+    """The gradient jobs of the plan (smx_plan.cpp section 11: per hot dimension the derivative polynomial over the terms
+    that carry a coefficient, per cold block the row sums of its value items; every entry of J written by exactly one job):
+    equal to the reference's gradient wherever that one is finite, finite at the nodes, and at least as close to the 80-bit
+    referee."""
     g = load(case)
     if case in LAYOUT_CASES:
         layout = golden_layout(g)
@@ -242,19 +244,3 @@ def test_compact_layout_reuses_f_evals():
     again = SmolyakBarycentricInterpolator(**kwargs)
     layout, _ = again._assemble_compact(lambda x: 1 / 0, evals)  # nothing new to evaluate
     assert again.n_f_evals_new == 0 and layout["values"].shape[0] in (again.n_f_evals, again.n_f_evals - 1)
-
-
-@pytest.mark.parametrize("case", WELL_CONDITIONED)
-def test_dense_gradient_columns_match_the_sparse_sets(case):
-    """Derivative sets as columns of the dense product (hot dimensions) + block-sparse row sums (cold dimensions):
-    the same Jacobian as with block-sparse derivative sets, up to the summation order."""
-    g = load(case)
-    layout = _layout_of(g)
-    d_in, d_out = g["x"].shape[1], int(g["d_out"])
-    x = g["x"][: len(g["J_ref"])]
-    a = Plan(layout, d_in, d_out, GRADIENT | SPARSE | DENSE_GRADIENT)
-    b = Plan(layout, d_in, d_out, GRADIENT | SPARSE)
-    assert a.error is None and b.error is None
-    Ja, Jb = a.gradient(x), b.gradient(x)
-    scale = max(1.0, float(np.max(np.abs(Jb))))
-    assert np.max(np.abs(Ja - Jb)) <= 1e-12 * scale
