@@ -245,12 +245,20 @@ grad_kernel(const __grid_constant__ CUtensorMap xmap, const GradArgs a, const do
                                 const long long p = (long long)p0 + gid + 8 * i;
                                 if (p < a.N) {
                                     double* jr = J + (p * n_out + o) * a.d_in + job.z + 4 * tig;
-                                    const double g4[4] = {acc[i][0][0], acc[i][0][1], acc[i][1][0], acc[i][1][1]};
+                                    double g4[4] = {acc[i][0][0], acc[i][0][1], acc[i][1][0], acc[i][1][1]};
                                     const double x4[4] = {q0[i].x, q0[i].y, q1[i].x, q1[i].y};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
-                                        if (m4 >> e & 1)
-                                            jr[e] = (a.nan_at_nodes && (x4[e] == n0[e] || x4[e] == n1[e])) ? __longlong_as_double(0x7ff8000000000000ll) : g4[e];
+                                        if (a.nan_at_nodes && (x4[e] == n0[e] || x4[e] == n1[e])) g4[e] = __longlong_as_double(0x7ff8000000000000ll);
+                                    // the lane's four columns are one 32-byte sector of J: written whole when it may be (a
+                                    // partial sector makes L2 fetch the rest from HBM before it can write it back)
+                                    if (m4 == 15 && (reinterpret_cast<unsigned long long>(jr) & 31) == 0) {
+                                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(jr), "d"(g4[0]), "d"(g4[1]), "d"(g4[2]), "d"(g4[3]) : "memory");
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e)
+                                            if (m4 >> e & 1) jr[e] = g4[e];
+                                    }
                                 }
                             }
                         }

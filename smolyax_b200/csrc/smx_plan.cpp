@@ -734,6 +734,30 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         std::vector<int32_t> rows;
         std::vector<double> coef;
     };
+    // A table row as the kernels without product rows see it: the hot rows whose product it is (itself, if it is one).
+    // Shared-memory bank of a row's 16-byte pieces: (row * kTabPitch * 2) mod 32 words = 8 * (row mod 4) - the four lanes
+    // (tig) that fetch the four rows of a DMMA k-step in ONE LDS.128 are conflict free iff their rows differ modulo 4.
+    const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
+    const int32_t n_flat8 = (int32_t)(plan.tab_factors8.size() / 8);
+    auto row_factors = [&](int32_t row, int32_t* out) -> int {
+        if (row < flat_begin) {
+            out[0] = row;
+            return 1;
+        }
+        const int32_t k = row - flat_begin;
+        int n = 0;
+        if (k < n_flat8)
+            for (int i = 0; i < 8; ++i)
+                if (plan.tab_factors8[(size_t)k * 8 + i]) out[n++] = plan.tab_factors8[(size_t)k * 8 + i];
+        return n;  // 0: deeper than eight pairs (product rows in the table only)
+    };
+    auto residues = [&](int32_t row) -> unsigned {
+        int32_t f[8];
+        const int n = row_factors(row, f);
+        unsigned m = 0;
+        for (int i = 0; i < n; ++i) m |= 1u << (f[i] & 3);
+        return n ? m : 1u << (row & 3);
+    };
     // (block, row, lane)-sorted non-zeros -> work items of at most kChunkRows rows; coefficient of term t and output o from `coef_fn`
     auto build_chunks = [&](const std::vector<Nz>& nzl, auto coef_fn, std::vector<Chunk>& chunks) {
         for (size_t i = 0; i < nzl.size();) {
@@ -753,16 +777,27 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                 ck.block = b;
                 ck.flags = block_flags(b) | (nch > 1 ? kChunkSplit : 0);
                 ck.coef.assign((r1 - r0) * (size_t)d_out * kBlockWidth, 0.0);
-                // order the rows so that every group of four (one DMMA k-step) has four different table-row residues
-                // modulo 4 as long as the item has them: with kTabPitch that makes the A-fragment loads conflict free
+                // order the rows so that every group of four (one DMMA k-step) can put four hot rows with different residues
+                // modulo 4 first in their factor lists (pack_item then orders the factors): conflict-free A-fragment loads
                 std::vector<size_t> order;
                 {
-                    std::vector<std::vector<size_t>> cls(4);
-                    for (size_t r = r0; r < r1; ++r) cls[rows[r].first & 3].push_back(r);
-                    size_t taken[4] = {0, 0, 0, 0};
-                    while (order.size() < r1 - r0)
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            if (taken[k4] < cls[k4].size()) order.push_back(cls[k4][taken[k4]++]);
+                    std::vector<size_t> rest;
+                    for (size_t r = r0; r < r1; ++r) rest.push_back(r);
+                    while (!rest.empty()) {
+                        unsigned used = 0;
+                        for (int slot = 0; slot < 4 && !rest.empty(); ++slot) {
+                            int best = -1, best_n = 99;  // the row with the fewest residues still free (but at least one)
+                            for (size_t q = 0; q < rest.size(); ++q) {
+                                const int n = __builtin_popcount(residues(rows[rest[q]].first) & ~used);
+                                if (n > 0 && n < best_n) best = (int)q, best_n = n;
+                            }
+                            if (best < 0) best = 0;
+                            const unsigned free_res = residues(rows[rest[(size_t)best]].first) & ~used;
+                            used |= free_res & (~free_res + 1);
+                            order.push_back(rest[(size_t)best]);
+                            rest.erase(rest.begin() + best);
+                        }
+                    }
                 }
                 for (size_t pos = 0; pos < order.size(); ++pos) {
                     const size_t r = order[pos];
@@ -821,8 +856,6 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
     // ---- 10. kernel-side packing: directory + one contiguous metadata record per work item ------------------------
     // item = (entry block `block`, `rows` table rows at rows_ptr, flags) -> dir (4 ints), meta (kMetaInts ints), fac2 (64 ints);
     // returns the k-mask.  Also records in the plan whether four resp. eight factors per row suffice.
-    const int32_t flat_begin = 1 + plan.n_hot_rows, n_flat = (int32_t)(plan.tab_factors.size() / 4);
-    const int32_t n_flat8 = (int32_t)(plan.tab_factors8.size() / 8);
     auto pack_item = [&](int32_t block, int32_t flags_in, const int32_t* rows_ptr, int32_t rows, const double* coef, int32_t first_slot,
                          int32_t* dir, int32_t* meta, int32_t* fac2, int32_t* flags_out) -> int32_t {
         const int32_t e0 = block * kBlockWidth;
@@ -837,31 +870,42 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                     }
         // every row slot as the product of up to four hot rows (row 0 = the ones row pads): the kernel variant without
         // product rows in the value table multiplies them on the fly.  nf = most factors of any row of the item.
+        // The order of a row's factors is free (a product): per k-step (row slots 4 s .. 4 s + 3 = the four lanes of one
+        // LDS.128) and factor position, the four hot rows are chosen with different residues modulo 4 where the rows allow it.
         int32_t nf = 1;
-        for (int32_t i = 0; i < kBlockWidth; ++i) {
-            int32_t* f4 = meta + 96 + 4 * i;
-            const int32_t row = i < rows ? rows_ptr[i] : 0;
-            if (row < flat_begin) {
-                f4[0] = row;
-            } else if (row - flat_begin < n_flat) {
-                int32_t cnt = 0;
-                for (int f = 0; f < 4; ++f) {
-                    f4[f] = plan.tab_factors[(size_t)(row - flat_begin) * 4 + f];
-                    if (f4[f] != 0) cnt = f + 1;
-                }
-                nf = std::max(nf, cnt);
-            } else {
-                plan.flat_ok = false;  // a hot part of five or more pairs: the four-factor kernels cannot run ..
-                if (row - flat_begin < n_flat8) {  // .. the eight-factor ("deep") one can: factors 5..8 go to a second list
-                    int32_t cnt = 0;
-                    for (int f = 0; f < 8; ++f) {
-                        const int32_t v = plan.tab_factors8[(size_t)(row - flat_begin) * 8 + f];
-                        (f < 4 ? f4[f] : fac2[4 * i + f - 4]) = v;
-                        if (v != 0) cnt = f + 1;
+        (void)n_flat;
+        for (int32_t s0 = 0; s0 < kBlockWidth; s0 += 4) {
+            int32_t fac[4][8];
+            int cnt[4];
+            bool taken[4][8] = {{false}};
+            for (int q = 0; q < 4; ++q) {
+                const int32_t row = s0 + q < rows ? rows_ptr[s0 + q] : 0;
+                cnt[q] = row_factors(row, fac[q]);
+                if (row >= flat_begin && cnt[q] > 4) plan.flat_ok = false;  // five or more pairs: the four-factor kernels cannot run ..
+                if (cnt[q] == 0) plan.flat_ok = false, plan.deep_ok = false;  // .. more than eight: nor the eight-factor one
+                nf = std::max(nf, cnt[q]);
+            }
+            for (int pos = 0; pos < 8; ++pos) {
+                unsigned used = 0;
+                int order4[4] = {0, 1, 2, 3};  // slots with the fewest factors left choose first
+                std::sort(order4, order4 + 4, [&](int a1, int a2) { return cnt[a1] - pos < cnt[a2] - pos; });
+                for (int qi = 0; qi < 4; ++qi) {
+                    const int q = order4[qi];
+                    int32_t v = 0;  // (the ones row pads)
+                    if (pos < cnt[q]) {
+                        int pick = -1;
+                        for (int f = 0; f < cnt[q]; ++f)
+                            if (!taken[q][f] && !(used >> (fac[q][f] & 3) & 1)) {
+                                pick = f;
+                                break;
+                            }
+                        for (int f = 0; f < cnt[q] && pick < 0; ++f)
+                            if (!taken[q][f]) pick = f;
+                        taken[q][pick] = true;
+                        v = fac[q][pick];
                     }
-                    nf = std::max(nf, cnt);
-                } else {
-                    plan.deep_ok = false;
+                    used |= 1u << (v & 3);
+                    (pos < 4 ? meta[96 + 4 * (s0 + q) + pos] : fac2[4 * (s0 + q) + pos - 4]) = v;
                 }
             }
         }

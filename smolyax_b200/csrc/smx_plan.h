@@ -135,9 +135,12 @@ struct FastPlan {
     std::vector<double> ent_eta0;        // first centre (pi_{j,1}(x) = x - eta0)
     std::vector<double> eta;             // centres, concatenated per dimension
 
-    // Value table, one row of 32 points per index:  [0] = 1,  [1 + hot_row(e)] = pi of hot entry e, where hot_row()
-    // transposes every aligned block of 16 entries as a 4 x 4 matrix (so that the four lanes that read "their e-th
-    // entry" of a hot block touch four consecutive rows, i.e. four different bank groups),
+    // Value table, one row of 32 points per index:  [0] = 1,  [1 + hot_row(e)] = pi of hot entry e.  The shared-memory bank
+    // group of a row is its index modulo 4 (kTabPitch); hot_row() rotates every group of four entries by its number, so
+    // that BOTH four consecutive entries (the cheapest hot pairs: the rows the cold items multiply with, one per lane of
+    // an A-fragment load) AND the entries e, e + 4, e + 8, e + 12 of a block (what the four lanes of a hot item read as
+    // "their e-th entry") sit in four different bank groups (measured before: 18 % of all shared-memory wavefronts of the
+    // headline kernel were conflicts of the first kind),
     // [1 + n_hot_rows ..) = products of >= 2 hot pairs ("rows" of level >= 2), each parent * hot:
     int32_t n_tab = 1;
     int32_t n_levels = 1;                // highest number of pairs in a hot part, plus one
@@ -200,7 +203,7 @@ struct PlanOptions {
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline int32_t hot_row(int32_t h) { return (h & ~15) | ((h & 3) << 2) | ((h >> 2) & 3); }
+inline int32_t hot_row(int32_t h) { return (h & ~3) | (((h >> 2) + h) & 3); }
 
 // Builds the plan.  Returns "" on success, otherwise an error message (invalid layout, singular node set ..).
 std::string build_fast_plan(int64_t d_in, int64_t d_out, const double* offset, const std::vector<GroupView>& groups,
