@@ -758,6 +758,68 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         for (int i = 0; i < n; ++i) m |= 1u << (f[i] & 3);
         return n ? m : 1u << (row & 3);
     };
+    // The four rows of one DMMA k-step (the four lanes `tig` of one LDS.128) with `nf` factor slots each: which factor of a row
+    // goes to which slot is free (a product; unused slots read the ones row), so choose it such that, slot by slot, the four
+    // table rows differ modulo 4 as far as possible.  Cost = shared-memory wavefronts per quarter warp, summed over the slots
+    // (nf = the best case).  Coordinate descent over the rows (each tries all its placements); more than four slots: the
+    // factors stay in their order.  Deterministic.
+    auto arrange4 = [&](const int32_t* rows4, int n_rows, int nf, int32_t (*out)[8]) -> int {
+        int32_t fac[4][8];
+        int cnt[4];
+        for (int q = 0; q < 4; ++q) {
+            cnt[q] = q < n_rows ? row_factors(rows4[q], fac[q]) : 0;
+            if (cnt[q] == 1 && fac[q][0] == 0) cnt[q] = 0;  // the ones row itself
+            for (int i = 0; i < 8; ++i) out[q][i] = i < cnt[q] ? fac[q][i] : 0;
+        }
+        auto cost = [&]() {
+            int c = 0;
+            for (int pos = 0; pos < nf; ++pos) {
+                int worst = 1;
+                for (int q = 1; q < 4; ++q) {
+                    int same = 1;  // distinct rows before q in the same bank group, q included
+                    bool dup = false;
+                    for (int q2 = 0; q2 < q; ++q2) {
+                        if (out[q2][pos] == out[q][pos]) dup = true;
+                        else if (((out[q2][pos] ^ out[q][pos]) & 3) == 0) {
+                            bool first = true;
+                            for (int q3 = 0; q3 < q2; ++q3) first = first && out[q3][pos] != out[q2][pos];
+                            same += first;
+                        }
+                    }
+                    if (!dup) worst = std::max(worst, same);
+                }
+                c += worst;
+            }
+            return c;
+        };
+        int best = cost();
+        if (nf > 4) return best;
+        for (int pass = 0; pass < 4 && best > nf; ++pass) {
+            bool better = false;
+            for (int q = 0; q < 4; ++q) {
+                if (cnt[q] == 0 || nf == 1) continue;
+                int slot[4], keep[4];
+                for (int i = 0; i < nf; ++i) slot[i] = i < nf - cnt[q] ? -1 : i - (nf - cnt[q]), keep[i] = out[q][i];
+                do {  // all placements of the cnt factors into the nf slots
+                    for (int i = 0; i < nf; ++i) out[q][i] = slot[i] < 0 ? 0 : fac[q][slot[i]];
+                    const int c = cost();
+                    if (c < best) {
+                        best = c, better = true;
+                        for (int i = 0; i < nf; ++i) keep[i] = out[q][i];
+                    }
+                } while (std::next_permutation(slot, slot + nf));
+                for (int i = 0; i < nf; ++i) out[q][i] = keep[i];
+            }
+            if (!better) break;
+        }
+        return best;
+    };
+    auto item_slots = [&](const std::vector<int32_t>& item_rows) {
+        int32_t f[8];
+        int nf = 1;
+        for (int32_t r : item_rows) nf = std::max(nf, row_factors(r, f));
+        return nf;
+    };
     // (block, row, lane)-sorted non-zeros -> work items of at most kChunkRows rows; coefficient of term t and output o from `coef_fn`
     auto build_chunks = [&](const std::vector<Nz>& nzl, auto coef_fn, std::vector<Chunk>& chunks) {
         for (size_t i = 0; i < nzl.size();) {
@@ -797,6 +859,35 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                             order.push_back(rest[(size_t)best]);
                             rest.erase(rest.begin() + best);
                         }
+                    }
+                }
+                {   // .. then swap rows between k-steps while that removes wavefronts (arrange4 = the cost pack_item will realise)
+                    std::vector<int32_t> ids;
+                    for (size_t r : order) ids.push_back(rows[r].first);
+                    const int nf = item_slots(ids), ng = (int)((ids.size() + 3) / 4);
+                    int32_t scratch[4][8];
+                    auto group_cost = [&](int g) { return arrange4(ids.data() + 4 * g, std::min<int>(4, (int)ids.size() - 4 * g), nf, scratch); };
+                    std::vector<int> gc((size_t)ng);
+                    int total = 0;
+                    for (int g = 0; g < ng; ++g) total += gc[(size_t)g] = group_cost(g);
+                    for (int pass = 0; pass < 3 && total > ng * nf && nf <= 4; ++pass) {
+                        bool better = false;
+                        for (size_t i1 = 0; i1 < ids.size(); ++i1)
+                            for (size_t i2 = i1 + 1; i2 < ids.size(); ++i2) {
+                                const int g1 = (int)(i1 / 4), g2 = (int)(i2 / 4);
+                                if (g1 == g2 || (gc[(size_t)g1] == nf && gc[(size_t)g2] == nf)) continue;
+                                std::swap(ids[i1], ids[i2]);
+                                const int c1 = group_cost(g1), c2 = group_cost(g2);
+                                if (c1 + c2 < gc[(size_t)g1] + gc[(size_t)g2]) {
+                                    total += c1 + c2 - gc[(size_t)g1] - gc[(size_t)g2];
+                                    gc[(size_t)g1] = c1, gc[(size_t)g2] = c2;
+                                    std::swap(order[i1], order[i2]);
+                                    better = true;
+                                } else {
+                                    std::swap(ids[i1], ids[i2]);
+                                }
+                            }
+                        if (!better) break;
                     }
                 }
                 for (size_t pos = 0; pos < order.size(); ++pos) {
@@ -874,39 +965,35 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         // LDS.128) and factor position, the four hot rows are chosen with different residues modulo 4 where the rows allow it.
         int32_t nf = 1;
         (void)n_flat;
+        for (int32_t r = 0; r < rows; ++r) {
+            int32_t f[8];
+            const int cnt = row_factors(rows_ptr[r], f);
+            if (rows_ptr[r] >= flat_begin && cnt > 4) plan.flat_ok = false;  // five or more pairs: the four-factor kernels cannot run ..
+            if (cnt == 0) plan.flat_ok = false, plan.deep_ok = false;          // .. more than eight: nor the eight-factor one
+            nf = std::max(nf, cnt);
+        }
         for (int32_t s0 = 0; s0 < kBlockWidth; s0 += 4) {
-            int32_t fac[4][8];
-            int cnt[4];
-            bool taken[4][8] = {{false}};
-            for (int q = 0; q < 4; ++q) {
-                const int32_t row = s0 + q < rows ? rows_ptr[s0 + q] : 0;
-                cnt[q] = row_factors(row, fac[q]);
-                if (row >= flat_begin && cnt[q] > 4) plan.flat_ok = false;  // five or more pairs: the four-factor kernels cannot run ..
-                if (cnt[q] == 0) plan.flat_ok = false, plan.deep_ok = false;  // .. more than eight: nor the eight-factor one
-                nf = std::max(nf, cnt[q]);
-            }
-            for (int pos = 0; pos < 8; ++pos) {
-                unsigned used = 0;
-                int order4[4] = {0, 1, 2, 3};  // slots with the fewest factors left choose first
-                std::sort(order4, order4 + 4, [&](int a1, int a2) { return cnt[a1] - pos < cnt[a2] - pos; });
-                for (int qi = 0; qi < 4; ++qi) {
-                    const int q = order4[qi];
-                    int32_t v = 0;  // (the ones row pads)
-                    if (pos < cnt[q]) {
-                        int pick = -1;
-                        for (int f = 0; f < cnt[q]; ++f)
-                            if (!taken[q][f] && !(used >> (fac[q][f] & 3) & 1)) {
-                                pick = f;
-                                break;
-                            }
-                        for (int f = 0; f < cnt[q] && pick < 0; ++f)
-                            if (!taken[q][f]) pick = f;
-                        taken[q][pick] = true;
-                        v = fac[q][pick];
+            int32_t placed[4][8];
+            arrange4(rows_ptr + s0, std::max(0, std::min(4, rows - s0)), nf, placed);
+            for (int q = 0; q < 4; ++q)
+                for (int pos = 0; pos < 8; ++pos) (pos < 4 ? meta[96 + 4 * (s0 + q) + pos] : fac2[4 * (s0 + q) + pos - 4]) = placed[q][pos];
+        }
+        for (int32_t s0 = 0; s0 < rows; s0 += 4) {  // statistics: shared-memory wavefronts (per quarter warp) of the factor loads
+            ++plan.bank_stats[3];
+            for (int pos = 0; pos < nf; ++pos) {
+                int32_t v[4];
+                for (int q = 0; q < 4; ++q) v[q] = pos < 4 ? meta[96 + 4 * (s0 + q) + pos] : fac2[4 * (s0 + q) + pos - 4];
+                int worst = 0, worst_real = 0;
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    int n = 0, n_real = 0;
+                    for (int q = 0; q < 4; ++q) {
+                        bool seen = false;
+                        for (int q2 = 0; q2 < q; ++q2) seen = seen || v[q2] == v[q];
+                        if (!seen && (v[q] & 3) == r4) ++n, n_real += v[q] != 0;
                     }
-                    used |= 1u << (v & 3);
-                    (pos < 4 ? meta[96 + 4 * (s0 + q) + pos] : fac2[4 * (s0 + q) + pos - 4]) = v;
+                    worst = std::max(worst, n), worst_real = std::max(worst_real, n_real);
                 }
+                ++plan.bank_stats[0], plan.bank_stats[1] += worst, plan.bank_stats[2] += std::max(1, worst_real);
             }
         }
         int32_t flags = flags_in;
@@ -1271,6 +1358,7 @@ void smxh_plan_stats(void* p, int64_t* out) {
     (void)pl->n_tab;
     std::memcpy(out, v, sizeof(v));
 }
+void smxh_plan_bank_stats(void* p, int64_t* out) { std::memcpy(out, static_cast<smx::FastPlan*>(p)->bank_stats, 4 * sizeof(int64_t)); }
 // gradient jobs: out = [n_jobs, n_items, k-steps of all items, cold jobs, most items of a job, most k-steps of a job, zero ranges]
 void smxh_plan_grad_stats(void* p, int64_t* out) {
     auto* pl = static_cast<smx::FastPlan*>(p);
