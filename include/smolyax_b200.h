@@ -175,6 +175,10 @@ int smx_get_info(const smx_interp* h, smx_info* info);
 
 /* Number of kernels this library has launched in the calling process (bench.py reports it as gpu_launches). */
 int64_t smx_launch_count(void);
+/* Name and template arguments of the last kernel the calling thread launched through this library, e.g.
+ * "dense_eval_kernel<16,4,2,1>" (tests assert that a configuration ran on the kernel shape it was written for; bench.py
+ * records it next to every timing).  "" before the first launch. */
+const char* smx_last_kernel(void);
 
 const char* smx_last_error(void); /* thread-local message of the last failing call */
 int smx_version(void);            /* 100 * major + minor; the binding checks it against the struct layouts it was written for */

@@ -238,7 +238,7 @@ CASES = {
     "cfg2": lambda: make_cfg("cfg2", "leja", 1_000, 1, 10_000, 64, 8),
     "cfg3": lambda: make_cfg("cfg3_dout16", "leja", 100, 16, 10_000, 16, 2),
     # cfg3 with enough outputs for the widest shape of the GEMM-regime kernel (16 warps x 4 output blocks = 512 columns per CTA)
-    "cfg3w": lambda: make_cfg("cfg3_dout520", "leja", 100, 520, 10_000, 72, 0),
+    "cfg3w": lambda: make_cfg("cfg3_dout520", "leja", 100, 520, 10_000, 72, 1),
     "cfg4": lambda: make_cfg("cfg4", "gh", 1_000, 10, 100_000, 64, 8),
     # cfg5 = the cfg2 index set with 100 outputs (narrow shape of the GEMM-regime kernel); 257 points: a ragged last tile
     "cfg5": lambda: make_cfg("cfg5", "leja", 1_000, 100, 10_000, 257, 1),

@@ -85,6 +85,7 @@ EXPORTS = {
     "smx_basis": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "smx_get_info": (c_int, [c_void_p, POINTER(Info)]),
     "smx_launch_count": (c_int64, []),
+    "smx_last_kernel": (c_char_p, []),
     "smx_last_error": (c_char_p, []),
     "smx_version": (c_int, []),
     "smx_arch": (c_char_p, []),
@@ -197,3 +198,9 @@ def info(handle) -> dict:
     out = Info()
     check(lib.smx_get_info(handle, ctypes.byref(out)), "smx_get_info")
     return {name: int(getattr(out, name)) for name, _ in Info._fields_}
+
+
+def last_kernel() -> str:
+    """Name and template arguments of the last kernel this thread launched (smx_last_kernel)."""
+    return lib.smx_last_kernel().decode()
+

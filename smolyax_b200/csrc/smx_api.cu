@@ -10,6 +10,7 @@ namespace smx {
 
 static thread_local std::string t_error;
 std::atomic<int64_t> g_launches{0};
+thread_local char t_last_kernel[96] = "";
 
 void set_error(const std::string& msg) { t_error = msg; }
 int fail(int status, const std::string& msg) {
@@ -501,6 +502,7 @@ int smx_basis(const double* x, int64_t N, const double* xi, const double* w, int
 }
 
 int64_t smx_launch_count(void) { return g_launches.load(); }
+const char* smx_last_kernel(void) { return t_last_kernel; }
 const char* smx_last_error(void) { return t_error.c_str(); }
 int smx_version(void) { return 200; }
 const char* smx_arch(void) { return "sm_100a"; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdio>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@ void set_error(const std::string& msg);
 int fail(int status, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 extern std::atomic<int64_t> g_launches;
+extern thread_local char t_last_kernel[96];  // name and template arguments of the last kernel this thread launched
 
 #define SMX_CUDA(call)                                        \
     do {                                                      \
@@ -24,11 +26,14 @@ extern std::atomic<int64_t> g_launches;
         if (e__ != cudaSuccess) return smx::cuda_fail(e__, #call); \
     } while (0)
 
-#define SMX_LAUNCH_CHECK(name)                                \
-    do {                                                      \
-        smx::g_launches.fetch_add(1, std::memory_order_relaxed); \
-        cudaError_t e__ = cudaGetLastError();                 \
-        if (e__ != cudaSuccess) return smx::cuda_fail(e__, name); \
+// after every kernel launch: count it, remember which kernel (and which instantiation) it was - smx_last_kernel() - and
+// turn a launch error into a status.  Arguments: a printf format and its values.
+#define SMX_LAUNCH_CHECK(...)                                                        \
+    do {                                                                             \
+        smx::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
+        std::snprintf(smx::t_last_kernel, sizeof(smx::t_last_kernel), __VA_ARGS__);  \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) return smx::cuda_fail(e__, smx::t_last_kernel);      \
     } while (0)
 
 constexpr int kSeamMaxN = 8;  // active dimensions per summand supported by the per-summand kernels

@@ -353,7 +353,7 @@ int launch_splitk_(const DenseArgs& a, const double* x, double* y, cudaStream_t 
     const long long tiles = (a.N + kDenseTile - 1) / kDenseTile;
     const int groups = (a.nblk + NBT - 1) / NBT;
     dense_splitk_kernel<NW, NBT, FULL><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
-    SMX_LAUNCH_CHECK("dense_splitk_kernel");
+    SMX_LAUNCH_CHECK("dense_splitk_kernel<%d,%d,%d>", NW, NBT, (int)FULL);
     return SMX_OK;
 }
 
@@ -376,7 +376,7 @@ int launch(const DenseArgs& a, const double* x, double* y, cudaStream_t st) {
     const long long tiles = (a.N + kDenseTile - 1) / kDenseTile;
     const int groups = (a.nblk + NW * NB - 1) / (NW * NB);
     dense_eval_kernel<NW, NB, PF, CTAS><<<dim3((unsigned)tiles, (unsigned)groups), NW * 32, smem, st>>>(a, x, y);
-    SMX_LAUNCH_CHECK("dense_eval_kernel");
+    SMX_LAUNCH_CHECK("dense_eval_kernel<%d,%d,%d,%d>", NW, NB, PF, CTAS);
     return SMX_OK;
 }
 

@@ -619,7 +619,7 @@ int launch(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const
     if (EARLY != 2 || FLAT)
         SMX_CUDA(cudaFuncSetAttribute(fast_eval_kernel<NW, CTAS, EARLY, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(d, NW, FLAT)));
     fast_eval_kernel<NW, CTAS, EARLY, FLAT><<<(unsigned)grid, NW * 32, smem_bytes(d, NW, FLAT), st>>>(map, a, x, y);
-    SMX_LAUNCH_CHECK("fast_eval_kernel");
+    SMX_LAUNCH_CHECK("fast_eval_kernel<%d,%d,%d,%d>", NW, CTAS, (int)EARLY, (int)FLAT);
     return SMX_OK;
 }
 
@@ -635,7 +635,7 @@ int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
     const size_t smem = lean_smem_bytes(d, NW, DEEP);
     SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, y);
-    SMX_LAUNCH_CHECK("fast_lean_kernel");
+    SMX_LAUNCH_CHECK("fast_lean_kernel<%d,%d,%d,%d,%d,%d>", NW, (int)ETA0, (int)PRE1, (int)ELECT, (int)DEEP, (int)ONE);
     return SMX_OK;
 }
 template <int NW>

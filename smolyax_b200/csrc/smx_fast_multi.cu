@@ -245,7 +245,7 @@ int launch_multi(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
     SMX_CUDA(cudaFuncSetAttribute(fast_multi_kernel<NW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = std::min<long long>(a.num_tiles, (long long)d.sm_count);
     fast_multi_kernel<NW, S><<<(unsigned)grid, NW * 32, smem, st>>>(map, a, x, y);
-    SMX_LAUNCH_CHECK("fast_multi_kernel");
+    SMX_LAUNCH_CHECK("fast_multi_kernel<%d,%d>", NW, S);
     return SMX_OK;
 }
 

@@ -394,7 +394,7 @@ int launch_pipe(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, 
     SMX_CUDA(cudaFuncSetAttribute(fast_pipe_kernel<ETA0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = std::min<long long>(a.num_tiles, d.sm_count);
     fast_pipe_kernel<ETA0><<<(unsigned)grid, (a.nwk + 1) * 32, smem, st>>>(map, a, x, y);
-    SMX_LAUNCH_CHECK("fast_pipe_kernel");
+    SMX_LAUNCH_CHECK("fast_pipe_kernel<%d> workers=%d", (int)ETA0, a.nwk);
     return SMX_OK;
 }
 

@@ -325,7 +325,7 @@ int launch_grad(const CUtensorMap& map, const GradArgs& a, int sm_count, const d
     // fewer tiles than CTA slots: spread the outputs over gridDim.y instead of walking them one after the other
     const long long gy = a.num_tiles < slots ? std::min<long long>(a.d_out, (slots + a.num_tiles - 1) / a.num_tiles) : 1;
     grad_kernel<NW, ETA0><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, J);
-    SMX_LAUNCH_CHECK("grad_kernel");
+    SMX_LAUNCH_CHECK("grad_kernel<%d,%d>", NW, (int)ETA0);
     return SMX_OK;
 }
 

@@ -12,6 +12,10 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 ALL_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
 LAYOUT_CASES = [c for c in ALL_CASES if c.startswith(("small", "medium"))]
 BIG_CASES = [c for c in ALL_CASES if c not in LAYOUT_CASES]
+# zero-padded value tensors of the reference layout above 1 GiB: set_f assembles the compact layout (smx_create_compact), the
+# per-summand kernels and the oracle on the full layout are not run (the oracle runs on sampled output columns instead)
+COMPACT_CASES = {"cfg3_dout520"}
+REFERENCE_LAYOUT_CASES = [c for c in ALL_CASES if c not in COMPACT_CASES]
 # Non-nested rules of high degree whose hierarchical (Newton) form is refused by the plan compiler's conditioning check
 # (smx_plan.cpp newton_form_error: Gauss-Hermite degree 24 loses ~1e-10 of a cardinal function in fp64): the handle then runs
 # the per-summand barycentric kernels, i.e. the reference's own arithmetic.
