@@ -73,6 +73,34 @@ __global__ void mixed_chain(double* out, long long* cyc, int iters, double a, do
     if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
 
+// KM independent DMMAs and KF independent DFMAs per iteration: do the two share a pipe (time = sum) or not (time = max)?
+template <int KM, int KF>
+__global__ void mixed_indep(double* out, long long* cyc, int iters, double a, double b) {
+    double c[KM][2], f[KF];
+#pragma unroll
+    for (int k = 0; k < KM; ++k) c[k][0] = c[k][1] = threadIdx.x * 1e-9 + k;
+#pragma unroll
+    for (int k = 0; k < KF; ++k) f[k] = threadIdx.x * 1e-9 + k;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+            dmma(c[k], a, b);
+#pragma unroll
+            for (int j = 0; j < KF / KM; ++j) f[k * (KF / KM) + j] = fma(f[k * (KF / KM) + j], a, b);
+        }
+    }
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) s += c[k][0] + c[k][1];
+#pragma unroll
+    for (int k = 0; k < KF; ++k) s += f[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
 template <class F>
 static void run(const char* name, int ops_per_iter, int iters, F launch) {
     long long* cyc;
@@ -102,6 +130,9 @@ int main() {
         snprintf(nm, sizeof nm, "DMMA 4 independent accumulators"); run(nm, 4, iters, [&](long long* c) { dmma_indep<4><<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
         snprintf(nm, sizeof nm, "DMMA 8 independent accumulators"); run(nm, 8, iters, [&](long long* c) { dmma_indep<8><<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
         snprintf(nm, sizeof nm, "DMMA -> DFMA -> DMMA dependent (per pair)"); run(nm, 1, iters, [&](long long* c) { mixed_chain<<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
+        snprintf(nm, sizeof nm, "4 DMMA + 8 DFMA independent (per iteration)"); run(nm, 1, iters, [&](long long* c) { mixed_indep<4, 8><<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
+        snprintf(nm, sizeof nm, "4 DMMA + 16 DFMA independent (per iteration)"); run(nm, 1, iters, [&](long long* c) { mixed_indep<4, 16><<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
+        snprintf(nm, sizeof nm, "4 DMMA + 32 DFMA independent (per iteration)"); run(nm, 1, iters, [&](long long* c) { mixed_indep<4, 32><<<sms, th>>>(out, c, iters, 1.0000001, 1e-9); });
         snprintf(nm, sizeof nm, "LDS.128 dependent chain"); run(nm, 1, iters, [&](long long* c) { lds_chain<<<sms, th>>>(out, c, iters); });
     }
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));

@@ -978,6 +978,19 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
             for (int q = 0; q < 4; ++q)
                 for (int pos = 0; pos < 8; ++pos) (pos < 4 ? meta[96 + 4 * (s0 + q) + pos] : fac2[4 * (s0 + q) + pos - 4]) = placed[q][pos];
         }
+        {
+            int n_half[2] = {0, 0};
+            for (int32_t r = 0; r < rows; ++r)
+                for (int hb = 0; hb < 2; ++hb) {
+                    bool any = false;
+                    for (int64_t o = 0; o < d_out; ++o)
+                        for (int i = 0; i < kBlockWidth; ++i)
+                            if (((i >> 1) & 1) == hb && coef[((size_t)r * d_out + o) * kBlockWidth + i] != 0.0) any = true;
+                    n_half[hb] += any;
+                }
+            plan.bank_stats[4] += __builtin_popcount((unsigned)kmask);
+            plan.bank_stats[5] += (n_half[0] + 3) / 4 + (n_half[1] + 3) / 4;
+        }
         for (int32_t s0 = 0; s0 < rows; s0 += 4) {  // statistics: shared-memory wavefronts (per quarter warp) of the factor loads
             ++plan.bank_stats[3];
             for (int pos = 0; pos < nf; ++pos) {
@@ -1358,7 +1371,7 @@ void smxh_plan_stats(void* p, int64_t* out) {
     (void)pl->n_tab;
     std::memcpy(out, v, sizeof(v));
 }
-void smxh_plan_bank_stats(void* p, int64_t* out) { std::memcpy(out, static_cast<smx::FastPlan*>(p)->bank_stats, 4 * sizeof(int64_t)); }
+void smxh_plan_bank_stats(void* p, int64_t* out) { std::memcpy(out, static_cast<smx::FastPlan*>(p)->bank_stats, 6 * sizeof(int64_t)); }
 // gradient jobs: out = [n_jobs, n_items, k-steps of all items, cold jobs, most items of a job, most k-steps of a job, zero ranges]
 void smxh_plan_grad_stats(void* p, int64_t* out) {
     auto* pl = static_cast<smx::FastPlan*>(p);

@@ -175,7 +175,8 @@ struct FastPlan {
     std::vector<int32_t> hot_pos;        // entry index of hot pair (d, a), indexed hot_off[d] + a - 1 (hot entries are
                                          // stored degree-major: blocks of equal degree share most of their rows)
     std::vector<double> c0;              // (d_out) constant term, includes the offset
-    int64_t bank_stats[4] = {0, 0, 0, 0};  // A-fragment loads of all items: [loads, wavefront groups, the same without the ones row, k-steps]
+    int64_t bank_stats[6] = {0, 0, 0, 0, 0, 0};  // A-fragment loads of all items: [loads, wavefront groups, the same without the ones row, k-steps,
+                                                //  (k-step, half block) pairs executed, fewest possible for the items' rows]
     int64_t padded_fma = 0;              // FMAs per point and output the kernel executes: 32 per non-empty (k-step, half block)
     int32_t n_rows = 0;                  // distinct hot parts (statistics)
     bool has_sparse = false;             // work items + coefficient sets above are filled
