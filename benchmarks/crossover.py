@@ -30,7 +30,7 @@ def timed(fn, reps=5):
     return float(np.median(out))
 
 
-GRID = {"cfg2": ((1, 2, 3, 4, 6, 8, 10, 12, 16, 24, 32, 48, 64), 200_000), "cfg4": ((1, 2, 4, 8, 10, 16, 24, 32, 64), 100_000)}
+GRID = {"cfg2": ((1, 2, 3, 4, 6, 8, 10, 12, 16, 18, 20, 24, 28, 32, 48, 64), 200_000), "cfg4": ((1, 2, 4, 8, 10, 16, 18, 20, 24, 32, 64), 100_000)}
 for cfg in sys.argv[1:] or ["cfg2", "cfg4"]:
     douts, n = GRID[cfg]
     base = workloads.CONFIGS[cfg]
@@ -51,5 +51,5 @@ for cfg in sys.argv[1:] or ["cfg2", "cfg4"]:
         k_auto = _lib.last_kernel()
         err = float((ref(x) - alt(x)).abs().max())
         print(f"{cfg} d_out {d_out:3d}: sparse {t_sparse:8.3f} ms ({k_sparse}) dense {t_dense:8.3f} ms ({k_dense}) "
-              f"auto {t_auto:8.3f} ms = {n * d_out / t_auto / 1e6:7.1f} M evals/s ({k_auto})  maxdiff {err:.1e}", flush=True)
+              f"auto {t_auto:8.3f} ms = {n * d_out / t_auto / 1e3:7.1f} M evals/s ({k_auto})  maxdiff {err:.1e}", flush=True)
         del ref, alt, auto

@@ -1040,6 +1040,13 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
         plan.padded_fma += 32 * __builtin_popcount((unsigned)plan.chunk_kmask[c]);
     }
 
+    if (opt.dense && opt.dense_if_cheaper && plan.has_dense && (double)d_out * (double)plan.padded_fma < 29.0 * (double)plan.n_terms) {
+        plan.has_dense = false;  // (PlanOptions::dense_if_cheaper: one pass per output of the block-sparse kernel is cheaper)
+        plan.dense_k4 = 0;
+        std::vector<int32_t>().swap(plan.dense_meta);
+        std::vector<double>().swap(plan.dense_coef);
+    }
+
     // ---- 11. gradient: jobs -----------------------------------------------------------------------------------------------
     // A job produces columns of J for every point of a tile and is run by ONE warp, so nothing is ever added to J:
     //   kind 0, one per cold block: the row sums acc[p][e] = sum_r C[r][e] m_r(p) of the block's value items ARE dI/dx of
