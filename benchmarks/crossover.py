@@ -30,7 +30,7 @@ def timed(fn, reps=5):
     return float(np.median(out))
 
 
-GRID = {"cfg2": ((1, 2, 3, 4, 6, 8, 10, 12, 16, 18, 20, 24, 28, 32, 48, 64), 200_000), "cfg4": ((1, 2, 4, 8, 10, 16, 18, 20, 24, 32, 64), 100_000)}
+GRID = {"cfg2": ((1, 2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64), 200_000), "cfg4": ((1, 2, 4, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48, 64), 100_000)}
 for cfg in sys.argv[1:] or ["cfg2", "cfg4"]:
     douts, n = GRID[cfg]
     base = workloads.CONFIGS[cfg]

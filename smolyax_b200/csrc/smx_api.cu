@@ -133,7 +133,7 @@ PlanOptions plan_options(uint32_t flags, int64_t d_out, bool sparse_wanted) {
     PlanOptions opt;
     static const int dense_min = tune_int("SMX_DENSE_MIN", 32);
     opt.dense = (flags & SMX_DENSE_PATH) || (!(flags & SMX_NO_DENSE_PATH) && d_out >= dense_min);
-    if (!opt.dense && !(flags & SMX_NO_DENSE_PATH) && sparse_wanted && d_out >= 16 && d_out < dense_min)
+    if (!opt.dense && !(flags & SMX_NO_DENSE_PATH) && sparse_wanted && d_out >= 8 && d_out < dense_min)
         opt.dense = opt.dense_if_cheaper = true;  // decided by the plan compiler from the index set (smx_plan.h)
     // the block-sparse form stores every coefficient set padded to 16-entry blocks: beyond a few thousand outputs it
     // only costs memory once the dense form exists (it would still serve the gradient)

@@ -147,27 +147,37 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
         for (int j = 0; j < NB; ++j) bq[u][j] = j < nbv ? __ldg(bbase + boff[j] + u * 32) : 0.0;
 
-    auto stage_mma = [&](int s, auto full) {
+    // One instantiation per number of blocks the warp really has (the last warp of the last column group has fewer than NB):
+    // a DMMA that is predicated off still occupies the FP64 pipe for its 16 cycles (profiles/r06_k1_experiments.md, r08), so
+    // "j < nbv" must be resolved at compile time, not by a predicate.
+    auto stage_mma = [&](int s, auto nb_tag) {
+        constexpr int NBV = decltype(nb_tag)::value;
         const double2* af = reinterpret_cast<const double2*>(abuf + (s & 1) * NW * 128) + lane;
         const double* bp = bbase + (size_t)s * NW * 32;
 #pragma unroll
         for (int kk = 0; kk < NW; ++kk) {
             const double2 a01 = af[kk * 64], a23 = af[kk * 64 + 32];
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (decltype(full)::value || j < nbv) {
-                    dmma(acc[0][j], a01.x, bq[kk % PF][j]);
-                    dmma(acc[1][j], a01.y, bq[kk % PF][j]);
-                    dmma(acc[2][j], a23.x, bq[kk % PF][j]);
-                    dmma(acc[3][j], a23.y, bq[kk % PF][j]);
-                }
+            for (int j = 0; j < NBV; ++j) {
+                dmma(acc[0][j], a01.x, bq[kk % PF][j]);
+                dmma(acc[1][j], a01.y, bq[kk % PF][j]);
+                dmma(acc[2][j], a23.x, bq[kk % PF][j]);
+                dmma(acc[3][j], a23.y, bq[kk % PF][j]);
                 // refill the slot just consumed: the fragment of k-step kk + PF (no second register set needed).  Only the
                 // blocks this warp really has: the kernel runs at the L2 -> SM bandwidth limit (64 bytes of B per DMMA),
                 // a duplicate load of a clamped block costs as much as a useful one
-                if (decltype(full)::value || j < nbv) bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
+                bq[kk % PF][j] = __ldg(bp + boff[j] + (kk + PF) * 32);
             }
         }
     };
+    // (the 16-warp x 4-block shape is at its register limit: extra instantiations cost it spills - 615 vs 607 ms at cfg3 - and
+    // its only partial warp is the last one of the last of many column groups: that one multiplies its clamped duplicate blocks
+    // too and drops them in the epilogue)
+    auto stage_mma_any = [&](int s) {
+        if (nbv == NB || (NB == 4 && nbv > 0)) stage_mma(s, std::integral_constant<int, NB>());
+        else if (NB == 2 && nbv == 1) stage_mma(s, std::integral_constant<int, 1>());
+    };
+    static_assert(NB == 1 || NB == 2 || NB == 4, "partial warps: NB = 2 has its own instantiation, NB = 4 clamps (below)");
 
     for (int s = 0; s < n_stage; ++s) {
         const int2 mn = meta_of(s + (kSkew ? 3 : 2));
@@ -177,8 +187,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
         } else {
             load_cold(m1);  // for stage s + 1; consumed after the DMMAs below
         }
-        if (nbv == NB) stage_mma(s, std::true_type());
-        else if (nbv > 0) stage_mma(s, std::false_type());
+        stage_mma_any(s);
         if (!early) assemble(m1, (s + 1) & 1);
         if (kSkew) m1 = m2, m2 = mn;
         else m1 = mn;
@@ -402,9 +411,20 @@ int dense_kernel_launch(const DenseArgs& args, const double* x, double* y, cudaS
     // are 128 registers per thread), K split over the warps of a CTA
     // (measured: 0.76 vs 0.63 of the DMMA rate at 8 blocks; with two or more groups the staged kernel below wins)
     if (want_splitk != 0 && !want_nb && (a.nblk <= 8 || want_splitk > 0)) {
+        // one instantiation per number of blocks per group: a DMMA that is predicated off (block j >= nbv of a wider
+        // instantiation) still occupies the FP64 pipe for its 16 cycles - at 2 blocks on the 4-block kernel that was 60 % of
+        // the kernel's time (measured r08: cfg4 tables, d_out = 10: 4.98 ms per 10^5 points before)
         const int groups = (a.nblk + 7) / 8, per = (a.nblk + groups - 1) / groups;
-        if (per <= 4) return launch_splitk<16, 4>(a, x, y, st);
-        return launch_splitk<8, 8>(a, x, y, st);
+        switch (per) {
+            case 1: return launch_splitk<16, 1>(a, x, y, st);
+            case 2: return launch_splitk<16, 2>(a, x, y, st);
+            case 3: return launch_splitk<16, 3>(a, x, y, st);
+            case 4: return launch_splitk<16, 4>(a, x, y, st);
+            case 5: return launch_splitk<8, 5>(a, x, y, st);
+            case 6: return launch_splitk<8, 6>(a, x, y, st);
+            case 7: return launch_splitk<8, 7>(a, x, y, st);
+            default: return launch_splitk<8, 8>(a, x, y, st);
+        }
     }
     const bool two_fit = 2 * (dense_smem_bytes(a.n_tab, 8) + 1024) <= (size_t)smem_sm;
     int nb = a.nblk >= 48 ? 4 : a.nblk > 8 ? 2 : 1, nw = nb == 4 ? 16 : 8;

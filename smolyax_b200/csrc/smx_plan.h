@@ -199,10 +199,11 @@ struct PlanOptions {
     bool gradient = true;   // derivative jobs (GradPlan; needs the block-sparse form)
     bool sparse = true;     // block-sparse work items (K1; values and gradients)
     bool dense = false;     // dense term matrix (K2; values, large d_out)
-    // dense asked for by the d_out rule only (16 <= d_out < 32): kept if it is the cheaper form for THIS index set, dropped
-    // otherwise.  Measured on B200 (benchmarks/crossover.py, cfg2 and cfg4 tables): the split-K dense kernel costs
-    // 2.8e-12 s per term and point whatever d_out <= 32 (it is bound by assembling A, not by the DMMAs), one pass of the
-    // block-sparse kernel 1.0e-13 s per padded FMA, point and output  ->  dense wins from  d_out * padded_fma >= 29 * n_terms.
+    // dense asked for by the d_out rule only (8 <= d_out < 32): kept if it is the cheaper form for THIS index set, dropped
+    // otherwise.  Measured on B200 (benchmarks/crossover.py, profiles/r08_crossover.txt; cfg2 and cfg4 tables), seconds per
+    // point: split-K dense kernel  n_terms * (1.0e-12 + 3.7e-13 * blocks)  (assembling A, plus the DMMAs of ceil(d_out / 8)
+    // blocks of 8 outputs; the 16-warp x 4-block instantiation behaves like 5 blocks), block-sparse kernel, one pass per
+    // output:  1.0e-13 * padded_fma * d_out.
     bool dense_if_cheaper = false;
 };
 

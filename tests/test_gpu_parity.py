@@ -228,7 +228,7 @@ def test_values_dense_path(case):
     ("cfg1", "fast_pipe_kernel<1>", "grad_kernel<"),                # d_out = 1: the pipelined single-output kernel
     ("cfg2", "fast_pipe_kernel<1>", "grad_kernel<"),                # the headline configuration
     ("cfg4", "fast_", "grad_kernel<"),                              # Gauss-Hermite, 10 outputs
-    ("cfg3_dout16", "fast_", "grad_kernel<"),                       # 16 outputs: below the GEMM regime
+    ("cfg3_dout16", "dense_splitk_kernel<16,2,1>", "grad_kernel<"),  # 16 outputs = two blocks: K split over the warps of a CTA
     ("cfg5", "dense_eval_kernel<8,2,8,2>", "grad_kernel<"),         # d_in = 1000, d_out = 100: 8 warps x 2 blocks, skewed stages
     ("cfg3_dout520", "dense_eval_kernel<16,4,2,1>", "grad_kernel<"),  # cfg3's tables at 520 outputs: 16 warps x 4 blocks
 ])

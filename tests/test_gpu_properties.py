@@ -255,12 +255,12 @@ def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
     the CTA - same bits either way; (c) non-zero first centres (custom Leja domain) take the variant with the subtraction
     and still reproduce a polynomial exactly.  (The kernels' tuning knobs are compiled out of the product library.)"""
 
-    d_in, d_out = 24, 10  # below the GEMM regime: ten passes of the block-sparse kernel
+    d_in, d_out = 24, 10  # ten passes of the block-sparse kernel (dense=False: for so few terms the plan compiler would pick K2)
     k = workloads.anisotropy(d_in)
     gen = nodes.Leja(dim=d_in)
     t = indices.find_approximate_threshold(k, 700, True)
     f = workloads.TargetFamily(d_in, d_out)
-    ip = _interp(node_gen=gen, k=k, t=t, d_out=d_out, f=f, batched_f=True)
+    ip = _interp(node_gen=gen, k=k, t=t, d_out=d_out, f=f, batched_f=True, dense=False)
     assert ip.device_info()["has_fast_path"] == 1 and ip.device_info()["has_dense_path"] == 0
     x = torch.rand((40_000, d_in), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 2 - 1
     y_big = ip(x)                      # 1250 tiles: gridDim.y = 1
