@@ -420,6 +420,39 @@ def cfg5_sweep(args, world, rank, local, peaks):
     }
 
 
+def run_heatmap(args):
+    """the reference's benchmark grid (benchmarking/benchmark.py:33-36, 104-136) with a baseline column - per
+    cell the B200 path as the reference times its own (20 calls host NumPy -> host NumPy) and the CPU restatement of the
+    reference's algorithm (oracle, all host cores) on the same X; log10(t_cpu / t_b200) panels like benchmark.py:190-222.
+    The CPU leg is bounded: it evaluates the first --heatmap-cpu-points rows of X once (after a warm call) and scales
+    linearly to the cell's batch (the algorithm is a loop over points; said in every line's cpu_note)."""
+    sys.path.insert(0, str(ROOT / "benchmarks"))
+    import heatmap
+    from oracle import oracle
+
+    cores = oracle.use_all_cores()
+
+    def cpu_timer(layout, X):
+        n = min(len(X), args.heatmap_cpu_points)
+        xs = np.ascontiguousarray(X[:n])
+        oracle.evaluate(layout, xs[: min(n, 8)])
+        t0 = time.perf_counter()
+        oracle.evaluate(layout, xs)
+        dt = time.perf_counter() - t0
+        return dt * len(X) / n, f"oracle on {cores} cores, {n} of {len(X)} rows timed, scaled linearly"
+
+    lines, grid = heatmap.run_grid(quick=args.heatmap_quick, seed=0, cpu_timer=cpu_timer, cache_dir=args.heatmap_cache or None,
+                                   log=lambda s: print(s, file=sys.stderr, flush=True))
+    if args.heatmap_out:
+        Path(args.heatmap_out).write_text("".join(json.dumps(l) + "\n" for l in lines))
+    heatmap.print_panels(lines, grid)
+    heatmap.print_panels(lines, grid, key="log10_cpu_over_b200", title="log10(t_cpu / t_b200)", fmt="{:8.2f}")
+    ratios = [l["log10_cpu_over_b200"] for l in lines]
+    emit({"metric": "heat-map grid: log10(t_cpu / t_b200) per cell", "cells": len(lines), "min": min(ratios), "median": float(np.median(ratios)),
+          "max": max(ratios), "cpu_baseline": {"kind": "port", "cores": cores, "sample": f"first {args.heatmap_cpu_points} rows per cell, scaled"},
+          "protocol": "benchmarking/benchmark.py:104-136 (N_ITER = 20, host NumPy in and out)"})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,6 +468,11 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the records of the other configurations and the cfg5 sweep")
     ap.add_argument("--sweep-points", type=int, default=100_000_000, help="total points of the cfg5 sweep (BASELINE configs[4])")
     ap.add_argument("--standin-points", type=int, default=20_000)
+    ap.add_argument("--heatmap", action="store_true", help="run the reference's benchmark grid with a CPU baseline column instead")
+    ap.add_argument("--heatmap-quick", action="store_true", help="corners of the grid only")
+    ap.add_argument("--heatmap-out", default="", help="JSON lines, one per cell")
+    ap.add_argument("--heatmap-cache", default="", help="directory of per-cell .npz timings (reused when present)")
+    ap.add_argument("--heatmap-cpu-points", type=int, default=100)
     ap.add_argument("--shard", default="points", choices=["points", "columns"],
                     help="multi-GPU partition: points (weak scaling, tables replicated) or output columns (strong scaling: "
                          "every rank evaluates all points for its slice of the value table; for huge d_out)")
@@ -443,6 +481,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.heatmap:
+        return run_heatmap(args)
 
     import torch
     import torch.distributed as dist
