@@ -832,9 +832,11 @@ static std::string build_from_summands(int64_t d_in, int64_t d_out, const double
                 rows.push_back({nzl[j].row, {j, k2}});
                 j = k2;
             }
-            const size_t nr = rows.size(), nch = (nr + kChunkRows - 1) / kChunkRows;
-            for (size_t c = 0; c < nch; ++c) {  // split evenly into chunks of at most kChunkRows rows
-                const size_t r0 = c * nr / nch, r1 = (c + 1) * nr / nch;
+            // split into chunks of at most kChunkRows rows, evenly in whole k-steps of four rows (18 rows: 12 + 6 = 3 + 2 k-steps;
+            // cut in the middle, 9 + 9, they would pad to 3 + 3)
+            const size_t nr = rows.size(), nks = (nr + 3) / 4, nch = (nks + kChunkRows / 4 - 1) / (kChunkRows / 4);
+            for (size_t c = 0; c < nch; ++c) {
+                const size_t r0 = std::min(nr, 4 * (c * nks / nch)), r1 = std::min(nr, 4 * ((c + 1) * nks / nch));
                 Chunk ck;
                 ck.block = b;
                 ck.flags = block_flags(b) | (nch > 1 ? kChunkSplit : 0);
