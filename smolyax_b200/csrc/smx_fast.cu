@@ -146,8 +146,10 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
     auto build_directory = [&](int nw, std::vector<int32_t>& dir, int32_t* warp_off, bool pipe) {
         dir.assign((size_t)plan.n_chunks * 4, 0);
         // cost model of an item: fixed + per k-step + extra for streaming x (measured at the headline configuration, ms per
-        // 10^6 points: barrier kernels 2,1,0; pipelined kernel 2,1,0: 1.684, 2,1,1: 1.651, 1,1,1: 1.659, 3,1,1: 1.694, 2,1,2: 1.781)
-        double ca = 2.0, cb = 1.0, cc = pipe ? 1.0 : 0.0;
+        // 10^6 points: barrier kernels 2,1,0; pipelined kernel r06: 2,1,0: 1.684, 2,1,1: 1.651, 1,1,1: 1.659, 3,1,1: 1.694;
+        // r08, after the bank-group layout made the k-steps cheaper (tuning build, benchmarks/k1_sweep.sh): 2,1,1: 1.614,
+        // 3,1,1: 1.614, 3,1,1.5: 1.586, 2.5,1,2 / 3,1,2 / 3.5,1,2: 1.569, 3,1,2.5: 1.601, 4,1,2: 1.581, 6,1,3: 1.631)
+        double ca = pipe ? 3.0 : 2.0, cb = 1.0, cc = pipe ? 2.0 : 0.0;
         if (const char* env = tune_str("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf", &ca, &cb, &cc);
         auto cost = [&](int32_t c) {
             return ca + cb * (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4) + ((plan.chunk_flags[c] & kChunkHot) ? 0.0 : cc);
@@ -156,9 +158,21 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         for (int32_t c = 0; c < plan.n_chunks; ++c) by_cost[c] = c;
         std::stable_sort(by_cost.begin(), by_cost.end(), [&](int32_t x1, int32_t x2) { return cost(x1) > cost(x2); });
         std::vector<std::vector<int32_t>> lists((size_t)nw);
-        std::vector<double> load((size_t)nw, 0.0);
+        // Pipelined kernel: warp w runs on SM sub-partition w % 4 (profiles/smsp_map.cu) and the service warp is warp nw, so the
+        // workers that share its sub-partition have one DMMA-issuing competitor fewer.  Giving them proportionally more work
+        // (speed > 1) was measured and does not pay (r08, ms per 10^6 points at speed 0.8 / 0.9 / 1.0 / 1.15 / 1.25 / 1.5:
+        // 1.650 / 1.601 / 1.614 / 1.678 / 1.716 / 1.937): the knob stays for tuning builds, the default is no bonus.
+        std::vector<double> load((size_t)nw, 0.0), speed((size_t)nw, 1.0);
+        if (pipe) {
+            double bonus = 1.0;
+            if (const char* env = tune_str("SMX_PIPE_BONUS")) bonus = std::atof(env);
+            for (int w = 0; w < nw; ++w)
+                if (w % 4 == nw % 4) speed[(size_t)w] = bonus;
+        }
         for (int32_t c : by_cost) {
-            const size_t w = std::min_element(load.begin(), load.end()) - load.begin();
+            size_t w = 0;
+            for (size_t w2 = 1; w2 < (size_t)nw; ++w2)
+                if ((load[w2] + cost(c)) / speed[w2] < (load[w] + cost(c)) / speed[w]) w = w2;
             lists[w].push_back(c);
             load[w] += cost(c);
         }
