@@ -231,7 +231,7 @@ def gradient_parity(layout, xs, got):
     }
 
 
-def eval_roofline(info, d_in, d_loc, n_points, ms, peaks, peak_kind, launches_per_step=None, traffic=None, traffic_source=None):
+def eval_roofline(info, d_in, d_loc, n_points, ms, peaks, peak_kind, launches_per_step=None, traffic=None, traffic_source=None, kernel_name=None):
     """t_roof = max(bytes / BW, flops / FP64 rate) with bytes_eval = 8 (d_in + d_out) per point and the folded
     form's 2 * n_terms * d_out flops per point (padding is not counted)."""
     pk = fp64_peak()
@@ -242,7 +242,8 @@ def eval_roofline(info, d_in, d_loc, n_points, ms, peaks, peak_kind, launches_pe
     dense = bool(info["has_dense_path"])
     fma_per_eval = info["dense_terms"] if dense else info["padded_fma"]
     tensor_bound = dense or alg_flops / (pk * 1e12) > alg_bytes / (peaks["hbm_gbs"] * 1e9)
-    kernel = "dense_eval_kernel" if dense else ("fast_pipe_kernel" if d_loc == 1 else "fast_multi_kernel" if d_loc in (3, 5, 6) else "fast_lean_kernel")
+    # (smx_last_kernel(): the instantiation that really ran; the fallback names the family the dispatch rules would pick)
+    kernel = kernel_name or ("dense_eval_kernel" if dense else ("fast_pipe_kernel" if d_loc == 1 else "fast_multi_kernel" if d_loc in (3, 5, 6) else "fast_lean_kernel"))
     if tensor_bound:
         r = {"bound": "tensor", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk, "traffic": traffic,
              "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) rate measured with profiles/fp64_peaks.cu (MEASURED_PEAKS.json has no fp64 figure)",
@@ -331,18 +332,22 @@ def other_records(peaks, peak_kind, device):
             l0 = _lib.lib.smx_launch_count()
             ms = timed_ms(lambda: ip(x, out=y), 3 if name == "cfg3" else 5, warm=1 if name == "cfg3" else 2)
             launches = int(_lib.lib.smx_launch_count() - l0) // ((3 if name == "cfg3" else 5) + (1 if name == "cfg3" else 2))
+            kernel_eval = _lib.last_kernel()
             got = y[:64].cpu().numpy()
             if cols is not None:
                 got = got[:, cols]
             records.append({**base, "op": "eval", "points": n_eval, "ms": ms, "value": n_eval * wl.d_out / (ms * 1e-3), "unit": UNIT,
-                            "roofline": eval_roofline(info, wl.d_in, wl.d_out, n_eval, ms, peaks, peak_kind, launches),
+                            "kernel": kernel_eval, "launches_per_call": launches,
+                            "roofline": eval_roofline(info, wl.d_in, wl.d_out, n_eval, ms, peaks, peak_kind, launches, kernel_name=kernel_eval),
                             "parity": value_parity(check_layout, x[:64].cpu().numpy(), got)})
             if n_grad:
                 xg = x[:n_grad]
                 ms = timed_ms(lambda: ip.gradient(xg), 3, warm=1)
+                kernel_grad = _lib.last_kernel()
                 J = ip.gradient(xg[:8]).cpu().numpy()
                 records.append({**base, "op": "gradient", "points": n_grad, "ms": ms, "value": n_grad * wl.d_out * wl.d_in / (ms * 1e-3),
                                 "unit": "J entries/s", "points_per_s": n_grad / (ms * 1e-3),
+                                "kernel": kernel_grad,
                                 "roofline": gradient_roofline(wl, n_grad, ms, peaks),
                                 "parity": gradient_parity(check_layout, xg[:8].cpu().numpy(), J)})
             ms = timed_ms(lambda: ip.integral(), 5)
@@ -547,6 +552,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = int(_lib.lib.smx_launch_count() - launches0)
+    timed_kernel = _lib.last_kernel()  # the instantiation the timed steps ran
     elapsed_ms = sdist.max_over_ranks(start.elapsed_time(stop))
     ms_per_step = elapsed_ms / args.steps
     value = (1 if columns else world) * n_points * d_out / (ms_per_step * 1e-3)
@@ -607,7 +613,8 @@ def main():
                 traffic_source = tj.get("source") if traffic is not None else None
             except Exception:
                 traffic = None
-        roofline = eval_roofline(info, d_in, d_loc, n_points, ms_per_step, peaks, peak_kind, launches // max(args.steps, 1), traffic, traffic_source)
+        roofline = eval_roofline(info, d_in, d_loc, n_points, ms_per_step, peaks, peak_kind, launches // max(args.steps, 1), traffic, traffic_source,
+                                 kernel_name=timed_kernel)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns else "weak", "vs_baseline": None,
