@@ -378,7 +378,7 @@ def cfg5_sweep(args, world, rank, local, peaks):
 
     wl = workloads.CONFIGS["cfg5"]
     total = args.sweep_points
-    chunk = min(1_000_000, total)
+    chunk = min(500_000, total)  # 200 chunks at the default total: the same number of chunks per rank at 1, 2, 4 and 8 GPUs
     n_chunks = (total + chunk - 1) // chunk
     ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out, device=local, batched_f=True)
     layout = ip._assemble(wl.target(), {})[0] if rank == 0 else None
