@@ -335,7 +335,9 @@ int launch_grad(const CUtensorMap& map, const GradArgs& a, int sm_count, const d
 int grad_kernel_warps(const GradDevice& g, const FastDevice& d, int smem_sm) {
     GradArgs a{};
     a.n_items = g.n_items, a.n_jobs = g.n_jobs, a.n_hot = d.n_hot, a.n_hot_rows = d.n_hot_rows, a.hot_dims = d.hot_dims;
-    for (int nw : {8, 6, 4})
+    // (an 8-warp instantiation exists no more: at its 128-register cap it spilled 56-88 bytes per thread and lost to 6 warps
+    //  wherever both fit - r08: cfg1 0.067 vs 0.058 ms per 10^4 points, cfg2 0.426 vs 0.423 ms per 37 888)
+    for (int nw : {6, 4})
         if (2 * (grad_smem_bytes(a, nw) + 1024) <= (size_t)smem_sm) return nw;
     return 0;
 }
@@ -357,7 +359,6 @@ int grad_kernel_launch(const FastDevice& d, const GradDevice& g, const double* x
     for (int w = 0; w <= kMaxWarps; ++w) a.warp_off[w] = g.warp_off[w];
     const bool eta0 = d.eta0_zero;
     switch (g.warps) {
-        case 8: return eta0 ? launch_grad<8, true>(map, a, d.sm_count, x, J, st) : launch_grad<8, false>(map, a, d.sm_count, x, J, st);
         case 6: return eta0 ? launch_grad<6, true>(map, a, d.sm_count, x, J, st) : launch_grad<6, false>(map, a, d.sm_count, x, J, st);
         case 4: return eta0 ? launch_grad<4, true>(map, a, d.sm_count, x, J, st) : launch_grad<4, false>(map, a, d.sm_count, x, J, st);
     }
