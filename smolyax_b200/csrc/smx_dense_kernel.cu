@@ -95,20 +95,28 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
     for (int i = 0; i < 4; ++i) xoff[i] = (int)(min((long long)(gid + 8 * i), a.N - 1 - p0) * a.ldx);
     auto meta_of = [&](int stage) { return __ldg(a.meta + 4 * (stage * NW + warp) + tig); };
-    double xc[4] = {0.0, 0.0, 0.0, 0.0};
-    auto load_cold = [&](int2 m) {  // leading entry on a cold column: pi = x - eta0, straight from x
+    // Leading entry on a cold column: pi = x - eta0, straight from x.  load_cold only REQUESTS the coordinates (and the centre);
+    // the subtraction happens in assemble, a stage later.  Written as "xc = ldg(..) - e0" the compiler put the DADD right behind
+    // the loads, in front of the stage's DMMAs, and every warp waited there for L2 once per stage (ncu r08: 9 % of all samples
+    // on those DADDs with long-scoreboard stalls).  Measured r08, ms: cfg3 at full size (16 warps x 4 blocks) 616 -> 584, split-K
+    // kernel at cfg4's tables and 16 outputs 2.89 -> 2.76; the skewed 8-warp shapes LOSE 2.5 % (cfg5 77.1 -> 79.1) and keep
+    // the subtraction at the load.
+    constexpr bool kLateSub = NB == 4;
+    double xc[4] = {0.0, 0.0, 0.0, 0.0}, xe0 = 0.0;
+    auto load_cold = [&](int2 m) {
         if (m.y < 0) {
             const int dim = -1 - m.y;
             const double e0 = __ldg(a.eta0 + dim);
+            xe0 = kLateSub ? e0 : 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim) - e0;
+            for (int i = 0; i < 4; ++i) xc[i] = kLateSub ? __ldg(xt + xoff[i] + dim) : __ldg(xt + xoff[i] + dim) - e0;
         }
     };
     auto assemble = [&](int2 m, int buf) {
         double v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i];
+            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : (kLateSub ? xc[i] - xe0 : xc[i]);
             v[i] = tab[m.x * kTabPitch + gid + 8 * i] * lead;
         }
         // two 16-byte halves per lane, each half contiguous over the lanes: conflict-free stores here and loads below
@@ -259,19 +267,19 @@ dense_splitk_kernel(const DenseArgs a, const double* __restrict__ x, double* __r
 #pragma unroll
     for (int i = 0; i < 4; ++i) xoff[i] = (int)(min((long long)(gid + 8 * i), a.N - 1 - p0) * a.ldx);
     auto meta_of = [&](int g) { return __ldg(a.meta + 4 * g + tig); };  // (arrays are padded: look-ahead needs no check)
-    double xc[4] = {0.0, 0.0, 0.0, 0.0};
-    auto load_cold = [&](int2 m) {
+    double xc[4] = {0.0, 0.0, 0.0, 0.0}, xe0 = 0.0;
+    auto load_cold = [&](int2 m) {  // (requests only; the subtraction waits until assemble - see dense_eval_kernel)
         if (m.y < 0) {
             const int dim = -1 - m.y;
-            const double e0 = __ldg(a.eta0 + dim);
+            xe0 = __ldg(a.eta0 + dim);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim) - e0;
+            for (int i = 0; i < 4; ++i) xc[i] = __ldg(xt + xoff[i] + dim);
         }
     };
     auto assemble = [&](int2 m, double (&v)[4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i];
+            const double lead = m.y >= 0 ? tab[m.y * kTabPitch + gid + 8 * i] : xc[i] - xe0;
             v[i] = tab[m.x * kTabPitch + gid + 8 * i] * lead;
         }
     };

@@ -201,7 +201,7 @@ struct PlanOptions {
     bool dense = false;     // dense term matrix (K2; values, large d_out)
     // dense asked for by the d_out rule only (8 <= d_out < 32): kept if it is the cheaper form for THIS index set, dropped
     // otherwise.  Measured on B200 (benchmarks/crossover.py, profiles/r08_crossover.txt; cfg2 and cfg4 tables), seconds per
-    // point: split-K dense kernel  n_terms * (1.0e-12 + 3.7e-13 * blocks)  (assembling A, plus the DMMAs of ceil(d_out / 8)
+    // point: split-K dense kernel  n_terms * (0.955e-12 + 3.53e-13 * blocks)  (assembling A, plus the DMMAs of ceil(d_out / 8)
     // blocks of 8 outputs; the 16-warp x 4-block instantiation behaves like 5 blocks), block-sparse kernel, one pass per
     // output:  1.0e-13 * padded_fma * d_out.
     bool dense_if_cheaper = false;
