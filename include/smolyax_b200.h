@@ -85,14 +85,14 @@ typedef struct {
 typedef struct {
     int64_t n_summands;
     const int32_t* n_active;  /* (n_summands) */
-    const int64_t* slot_off;  /* (n_summands + 1) */
+    const int64_t* slot_off;  /* (n_summands + 1), slot_off[0] = 0 */
     const int64_t* dims;      /* (slots) */
     const int64_t* degs;      /* (slots) */
     const int64_t* node_off;  /* (slots) */
     const double* node_pool;
     const double* quad_pool;  /* NULL: smx_integral is not available on the handle */
     const int64_t* zetas;     /* (n_summands) */
-    const int64_t* val_off;   /* (n_summands + 1) */
+    const int64_t* val_off;   /* (n_summands + 1), val_off[0] = 0 */
     const int64_t* val_index;
     const double* values;     /* (n_values, d_out) row-major */
     int64_t n_values;

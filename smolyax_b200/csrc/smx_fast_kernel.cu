@@ -479,12 +479,8 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                             q0[i] = *reinterpret_cast<const double2*>(xlo + i * (8 * kBlockWidth));
                             q1[i] = *reinterpret_cast<const double2*>(xhi + i * (8 * kBlockWidth));
                         }
-                        if (!ETA0 && !(dir.z & kChunkEtaZero)) {
-                            const double2 ea = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig);
-                            const double2 eb = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig + 16);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) q0[i].x -= ea.x, q0[i].y -= ea.y, q1[i].x -= eb.x, q1[i].y -= eb.y;
-                        }
+                        // (pi = x - eta_0: the subtraction waits until after the DMMAs - its 16 DADDs share the FP64 pipe with
+                        // them and would sit in front of the item's first DMMA; the centres stay in the item buffer until then)
                     }
                     __syncwarp();  // every lane has taken its x values: the x buffer and the other item buffer are free
                     if (ELECT) {  // one elected lane, warp-uniform operands: no per-lane-value loops around the copy instructions
@@ -550,6 +546,12 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
                             tot[i] = fma(v[i][3], acc[i][1][1], tot[i]);
                         }
                     } else {
+                        if (!ETA0 && !(dir.z & kChunkEtaZero)) {
+                            const double2 ea = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig);
+                            const double2 eb = *reinterpret_cast<const double2*>(ibt + offsetof(ItemBuffer, eta0) + 16 * tig + 16);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) q0[i].x -= ea.x, q0[i].y -= ea.y, q1[i].x -= eb.x, q1[i].y -= eb.y;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             tot[i] = fma(q0[i].x, acc[i][0][0], tot[i]);

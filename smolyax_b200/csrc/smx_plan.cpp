@@ -148,6 +148,9 @@ std::string compact_summands(int64_t d_out, const CompactView& cv, std::vector<S
     if (cv.n_summands < 0 || (cv.n_summands > 0 && (!cv.n_active || !cv.slot_off || !cv.dims || !cv.degs || !cv.node_off ||
                                                     !cv.node_pool || !cv.zetas || !cv.val_off || !cv.val_index || !cv.values)))
         return "compact descriptor has null arrays";
+    // CSR offsets start at 0 (the descriptor carries no array lengths: an offset array shifted as a whole would otherwise pass
+    // the per-summand difference checks and read past the end of val_index / dims)
+    if (cv.n_summands > 0 && (cv.slot_off[0] != 0 || cv.val_off[0] != 0)) return "slot_off / val_off must start at 0";
     for (int64_t s = 0; s < cv.n_summands; ++s) {
         Summand sm;
         sm.n = cv.n_active[s];
