@@ -149,10 +149,12 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         // 10^6 points: barrier kernels 2,1,0; pipelined kernel r06: 2,1,0: 1.684, 2,1,1: 1.651, 1,1,1: 1.659, 3,1,1: 1.694;
         // r08, after the bank-group layout made the k-steps cheaper (tuning build, benchmarks/k1_sweep.sh): 2,1,1: 1.614,
         // 3,1,1: 1.614, 3,1,1.5: 1.586, 2.5,1,2 / 3,1,2 / 3.5,1,2: 1.569, 3,1,2.5: 1.601, 4,1,2: 1.581, 6,1,3: 1.631)
-        double ca = pipe ? 3.0 : 2.0, cb = 1.0, cc = pipe ? 2.0 : 0.0;
-        if (const char* env = tune_str("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf", &ca, &cb, &cc);
+        double ca = pipe ? 3.0 : 2.0, cb = 1.0, cc = pipe ? 2.0 : 0.0, cd = 0.0;  // (cd: per k-step and factor beyond the first)
+        if (const char* env = tune_str("SMX_FAST_COST")) std::sscanf(env, "%lf,%lf,%lf,%lf", &ca, &cb, &cc, &cd);
         auto cost = [&](int32_t c) {
-            return ca + cb * (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4) + ((plan.chunk_flags[c] & kChunkHot) ? 0.0 : cc);
+            const double ks = (double)((plan.chunk_off[c + 1] - plan.chunk_off[c] + 3) / 4);
+            const double nf = (double)((plan.chunk_dir[(size_t)c * 4 + 2] >> 8) & 15);
+            return ca + (cb + cd * std::max(0.0, nf - 1.0)) * ks + ((plan.chunk_flags[c] & kChunkHot) ? 0.0 : cc);
         };
         std::vector<int32_t> by_cost((size_t)plan.n_chunks);
         for (int32_t c = 0; c < plan.n_chunks; ++c) by_cost[c] = c;
