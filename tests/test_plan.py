@@ -236,6 +236,27 @@ def test_compact_layout_gives_the_same_plan(case):
     np.testing.assert_allclose(q, g["Q_ref"], rtol=2e-9, atol=2e-9)  # the reference's own summation noise (test_oracle.py)
 
 
+def test_compact_descriptor_offsets_must_start_at_zero():
+    """The compact descriptor carries no array lengths: an offset array shifted as a whole passes every per-summand difference
+    check and would read past the end of val_index / dims (a GPU negative test was flaky on exactly that before the plan
+    compiler checked the first offsets).  Refused deterministically, with a message that names the arrays."""
+    g = load("small_02")
+    kwargs, f = interpolator_inputs(g)
+    d_in, d_out = g["x"].shape[1], int(g["d_out"])
+    good, _ = SmolyakBarycentricInterpolator(**kwargs)._assemble_compact(f, {})
+    assert Plan(good, d_in, d_out).error is None
+    for key in ("val_off", "slot_off"):
+        bad = dict(good)
+        # (padded so that even the shifted offsets stay inside the arrays this test owns)
+        bad[key] = np.ascontiguousarray(good[key] + 1)
+        bad["val_index"] = np.concatenate([good["val_index"], good["val_index"][-1:]])
+        bad["dims"] = np.concatenate([good["dims"], good["dims"][-1:]])
+        bad["degs"] = np.concatenate([good["degs"], good["degs"][-1:]])
+        bad["node_off"] = np.concatenate([good["node_off"], good["node_off"][-1:]])
+        plan = Plan(bad, d_in, d_out)
+        assert plan.error is not None and "must start at 0" in plan.error, plan.error
+
+
 def test_compact_layout_reuses_f_evals():
     g = load("small_03")
     kwargs, f = interpolator_inputs(g)
