@@ -105,6 +105,7 @@ struct FastDevice {
     bool deep_ok = false;  // hot parts of five to eight pairs: the plan carries a second factor list per row slot ..
     bool deep = false;     // .. and the eight-factor lean kernel is the one chosen (values only)
     int multi = 0;         // > 0: values run the multi-set kernel with that many coefficient sets per pass (2 <= d_out < 32)
+    int rest_warps = 0;    // > 0: outputs beyond a multiple of three run the lean kernel with that many warps (item lists: pipe_dir), the others fast_multi_kernel
     int pipe_warps = 0;    // > 0: single-output values run the pipelined kernel (smx_fast_pipe.cu) with that many worker warps ..
     int32_t pipe_warp_off[17] = {0};  // .. on their own per-warp item lists
     int32_t* pipe_dir = nullptr;

@@ -201,6 +201,9 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         if (dev.pipe_warps > 0) {  // the pipelined kernel has its own worker count, hence its own item lists
             build_directory(dev.pipe_warps, dir, dev.pipe_warp_off, true);
             if ((rc = upload(dir, &dev.pipe_dir, dev.bytes, 4))) return rc;
+        } else if (dev.rest_warps > 0) {  // .. and so has the lean kernel that takes the outputs the three-set kernel leaves over
+            build_directory(dev.rest_warps, dir, dev.pipe_warp_off, false);
+            if ((rc = upload(dir, &dev.pipe_dir, dev.bytes, 4))) return rc;
         }
     }
     if ((rc = upload(plan.tab_factors, &dev.tab_factors, dev.bytes, 4))) return rc;
@@ -264,6 +267,7 @@ int run_fast(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doubl
     a.N = N;
     a.ldx = ldx;
     a.d_out = d.d_out;
+    a.o_begin = 0, a.o_end = (int)d.d_out;
     a.num_tiles = (N + kTile - 1) / kTile;
     a.gradient = 0;
     a.d_in = d.d_in;

@@ -36,6 +36,7 @@ struct FastArgs {
     int flat;                // 1: the value table holds the hot rows only, product rows are multiplied on the fly
     int ablate;              // tuning builds only (SMX_TUNING): timing experiments, 0 in the product library
     int nwk;                 // pipelined kernel: number of worker warps (warp nwk is the service warp)
+    int o_begin, o_end;      // outputs [o_begin, o_end) of this launch (a call may split its outputs over two kernels: smx_fast_kernel.cu)
     unsigned long long* dbg; // tuning builds only: per-tile time stamps of CTA 0 (service warp and worker 0), else nullptr
     int level_off[kMaxLevels + 2];
     int warp_off[kMaxWarps + 1];  // work items of warp w are [warp_off[w], warp_off[w + 1]) of the (re-ordered) directory

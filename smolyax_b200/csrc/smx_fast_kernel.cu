@@ -405,9 +405,9 @@ fast_lean_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, con
         __syncthreads();
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);
 
-        const int n_out = ONE ? 1 : (int)a.d_out;  // ONE: single output, the set offset folds away in the staging code
+        const int n_out = ONE ? 1 : a.o_end;  // ONE: single output, the set offset folds away in the staging code
         // (outputs are spread over gridDim.y when there are fewer tiles than CTA slots: small batches, many outputs)
-        for (int o = ONE ? 0 : (int)blockIdx.y; o < n_out; o += ONE ? 1 : (int)gridDim.y) {
+        for (int o = ONE ? 0 : a.o_begin + (int)blockIdx.y; o < n_out; o += ONE ? 1 : (int)gridDim.y) {
             double tot[4] = {0.0, 0.0, 0.0, 0.0};
             int4 dir = make_int4(0, 0, 0, 0);
             const int4* dp = dir_begin;
@@ -633,7 +633,7 @@ template <int NW, bool ETA0, bool PRE1, bool ELECT, bool DEEP, bool ONE = false>
 int launch_lean2(const CUtensorMap& map, const FastArgs& a, const FastDevice& d, const double* x, double* y, cudaStream_t st) {
     const long long slots = (long long)d.sm_count * 2, grid = std::min<long long>(a.num_tiles, slots);
     // fewer tiles than CTA slots: split the outputs over gridDim.y instead of walking them one after the other
-    const long long gy = a.num_tiles < slots ? std::min<long long>(a.d_out, (slots + a.num_tiles - 1) / a.num_tiles) : 1;
+    const long long gy = a.num_tiles < slots ? std::min<long long>(a.o_end - a.o_begin, (slots + a.num_tiles - 1) / a.num_tiles) : 1;
     const size_t smem = lean_smem_bytes(d, NW, DEEP);
     SMX_CUDA(cudaFuncSetAttribute(fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fast_lean_kernel<NW, ETA0, PRE1, ELECT, DEEP, ONE><<<dim3((unsigned)grid, (unsigned)gy), NW * 32, smem, st>>>(map, a, x, y);
@@ -680,12 +680,19 @@ static int prepare_shape(FastDevice& d) {
     static const int want_flat = tune_int("SMX_FAST_FLAT", 1);
     d.flat = false;
     d.multi = 0;
+    d.rest_warps = 0;
     {   // a few outputs: several coefficient sets per pass (its warp count also fixes the per-warp item lists)
         int sets = 0, warps = 0;
         if (want_flat && want == 0 && multi_kernel_shape(d, smem_optin, &sets, &warps)) {
             d.flat = true;
             d.multi = sets;
             d.warps = warps;
+            // more than two passes and outputs left over beyond a multiple of `sets`: those run the single-set kernel in a
+            // second launch (its own warp count and item lists) instead of a pass with empty sets
+            d.rest_warps = 0;
+            if (d.d_out > 2 * sets && d.d_out % sets != 0)
+                for (int nw : {8, 6})
+                    if (d.rest_warps == 0 && 2 * (smem_bytes(d, nw, true) + 1024) <= (size_t)smem_sm) d.rest_warps = nw;
             return SMX_OK;
         }
     }
@@ -760,7 +767,18 @@ int fast_kernel_launch(const FastDevice& d, const FastArgs& a, const double* x, 
     const int rc_map = make_x_tensor_map(&map, x, d.d_in, a.N, a.ldx);
     if (rc_map) return rc_map;
     if (d.pipe_warps > 0 && a.N < (1ll << 31) - kTile) return pipe_kernel_launch(map, d, a, x, y, st);
-    if (d.multi) return multi_kernel_launch(map, d, a, x, y, st);
+    if (d.multi) {
+        if (d.rest_warps > 0 && a.N < (1ll << 31) - kTile) {
+            FastArgs am = a, al = a;
+            am.o_end = al.o_begin = (int)(d.d_out / d.multi) * d.multi;
+            const int rc = multi_kernel_launch(map, d, am, x, y, st);
+            if (rc) return rc;
+            al.chunk_dir = reinterpret_cast<const int4*>(d.pipe_dir);
+            for (int w = 0; w <= kMaxWarps; ++w) al.warp_off[w] = d.pipe_warp_off[w];
+            return d.rest_warps == 8 ? launch_lean<8>(map, al, d, x, y, st) : launch_lean<6>(map, al, d, x, y, st);
+        }
+        return multi_kernel_launch(map, d, a, x, y, st);
+    }
     if (d.flat) {
         // the lean item loop (SMX_FAST_LEAN=0 in a tuning build selects the general kernel, for A/B timing)
         static const int lean = tune_int("SMX_FAST_LEAN", 1);

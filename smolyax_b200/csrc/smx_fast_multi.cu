@@ -100,10 +100,10 @@ fast_multi_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, co
         __syncthreads();
         if (tile + gridDim.x < a.num_tiles) load_hot((tile + gridDim.x) * kTile);
 
-        const int n_pass = (int)((a.d_out + S - 1) / S);
+        const int n_pass = (a.o_end - a.o_begin + S - 1) / S;
         for (int pass = 0; pass < n_pass; ++pass) {
-            const long long set0 = (long long)pass * S;
-            const int ns = (int)min((long long)S, a.d_out - set0);
+            const long long set0 = a.o_begin + (long long)pass * S;
+            const int ns = (int)min((long long)S, a.o_end - set0);
             double tot[S][4];
 #pragma unroll
             for (int j = 0; j < S; ++j)
@@ -257,7 +257,12 @@ int launch_multi(const CUtensorMap& map, const FastArgs& a, const FastDevice& d,
 bool multi_kernel_shape(const FastDevice& d, int smem_optin, int* sets, int* warps) {
     static const int want = tune_int("SMX_FAST_MULTI", -1);  // 0: off; 2, 3: force
     if (want == 0 || !d.flat_ok || d.d_out < 2 || d.d_out >= 32) return false;
-    if (want < 0 && d.d_out > 6) return false;
+    // More than 6 outputs: only where a pass costs much more than its DMMAs - non-zero first centres (16 DADDs per cold item
+    // and pass) and hot parts of several pairs (DMULs per k-step and pass), i.e. Gauss-Hermite-like plans.  Measured r08 at cfg4's
+    // tables, ms per 1e5 points, one output per pass vs three: 9 outputs 2.31 vs 2.06, 12: 3.08 vs 2.69; at cfg2's tables
+    // (zero centres, 2e5 points) 9: 2.67 vs 2.62, 8: 2.38 vs 2.63.  The outputs beyond a multiple of three take the
+    // single-set kernel in a second launch (fast_kernel_launch).
+    if (want < 0 && d.d_out > 6 && d.eta0_zero) return false;
     // (measured against one output per pass of the lean kernel, cfg2 tables, ms per 1e6 points: 2 outputs 3.46 vs 3.29,
     //  3: 4.57 vs 4.75, 4: 6.52 vs 6.21, 6: 8.74 vs 9.13 - three sets per pass still pay, two no longer do)
     if (want < 0 && (d.d_out == 2 || d.d_out == 4)) return false;

@@ -203,7 +203,7 @@ struct PlanOptions {
     // otherwise.  Measured on B200 (benchmarks/crossover.py, profiles/r08_crossover.txt; cfg2 and cfg4 tables), seconds per
     // point: split-K dense kernel  n_terms * (0.955e-12 + 3.53e-13 * blocks)  (assembling A, plus the DMMAs of ceil(d_out / 8)
     // blocks of 8 outputs; the 16-warp x 4-block instantiation behaves like 5 blocks), block-sparse kernel, one pass per
-    // output:  1.0e-13 * padded_fma * d_out.
+    // output:  1.0e-13 * padded_fma * d_out  (0.91e-13 for plans with non-zero first centres, which run three outputs per pass).
     bool dense_if_cheaper = false;
 };
 
