@@ -156,14 +156,13 @@ fast_multi_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, co
                         v[0][e] = lo.x, v[1][e] = lo.y, v[2][e] = hi.x, v[3][e] = hi.y;
                     }
                 } else {
-                    const double2 ea = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig);
-                    const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
+                    // (raw coordinates: pi = x - eta_0 is subtracted after the DMMAs - its DADDs share their FP64 pipe and would sit
+                    // in front of the item's first DMMA; the centres stay in the record buffer until the item ends)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const double2 lo = *reinterpret_cast<const double2*>(xlo + i * (8 * kBlockWidth));
                         const double2 hi = *reinterpret_cast<const double2*>(xhi + i * (8 * kBlockWidth));
-                        if (dir.z & kChunkEtaZero) v[i][0] = lo.x, v[i][1] = lo.y, v[i][2] = hi.x, v[i][3] = hi.y;
-                        else v[i][0] = lo.x - ea.x, v[i][1] = lo.y - ea.y, v[i][2] = hi.x - eb.x, v[i][3] = hi.y - eb.y;
+                        v[i][0] = lo.x, v[i][1] = lo.y, v[i][2] = hi.x, v[i][3] = hi.y;
                     }
                 }
                 __syncwarp();  // every lane has taken its x values: the x buffer and the other record buffer are free
@@ -195,6 +194,12 @@ fast_multi_kernel(const __grid_constant__ CUtensorMap xmap, const FastArgs a, co
                             dmma_<0>(acc[j][i][1], af[i], b.y);
                         }
                     }
+                }
+                if (!(dir.z & (kChunkHot | kChunkEtaZero))) {
+                    const double2 ea = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig);
+                    const double2 eb = *reinterpret_cast<const double2*>(ib.eta0 + 4 * tig + 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i][0] -= ea.x, v[i][1] -= ea.y, v[i][2] -= eb.x, v[i][3] -= eb.y;
                 }
 #pragma unroll
                 for (int j = 0; j < S; ++j)
