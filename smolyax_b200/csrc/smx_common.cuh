@@ -95,6 +95,7 @@ struct FastDevice {
     int32_t* dense_meta = nullptr;
     double* dense_eta0 = nullptr;
     double* dense_coef = nullptr;
+    int32_t* dense_tickets = nullptr;  // one counter per SM: co-resident CTAs of the staged dense kernel rotate their block assignment (smx_dense_kernel.cu)
     bool eta0_zero = true;          // every cold block has zero first centres (pi_{j,1} = x_j): kernel variant without the subtraction
     bool has_cold = false;          // some leading entries live on cold columns (their derivatives are block-sparse row sums)
     int64_t bytes = 0;

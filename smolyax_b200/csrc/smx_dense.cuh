@@ -23,6 +23,7 @@ struct DenseArgs {
     int k4;                  // k-steps (4 terms each), a multiple of kDenseStageK4; arrays carry kDensePadK4 more (zeros)
     int nblk;                // ceil(ncol / 8)
     int n_tab, n_hot_rows, n_levels, hot_dims;
+    int32_t* tickets;        // per-SM CTA counters (256 ints, never reset), see dense_eval_kernel
     int skew;                // staged kernel: half of the warps assemble A before their DMMAs (set by dense_kernel_launch)
     int level_off[kMaxLevels + 2];
 };

@@ -74,15 +74,60 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     const int tig = lane & 3, gid = lane >> 2;
     const long long p0 = (long long)blockIdx.x * kDenseTile;
 
+    // ---- which output blocks this warp multiplies ---------------------------------------------------------------------------
+    // Dealt in warp order, a column group that does not fill the CTA loads the four FP64 pipes of the SM unevenly (cfg5: 13
+    // blocks on 8 warps x 2 -> 4, 4, 3, 2 blocks on the pipes of warps 0/4, 1/5, 2/6, 3/7), and the kernel takes as long as
+    // the fullest pipe: measured r08, 12, 13, 14 and 16 blocks all cost the time of 16 (38.6 / 38.6 / 39.1 / 40.2 ms per
+    // 5e5 points on cfg5's tables).  A warp's pipe is %warpid & 3 (profiles/smsp_map2.cu; the hardware places the warps of a
+    // second resident CTA in another rotation, different from launch to launch, so it has to be read, not assumed).  The
+    // partial group is therefore dealt per pipe - floor(blocks / 4) each, the remainder to a run of pipes that starts where
+    // the run of the CTA with the previous ticket on this SM ended, so that two resident CTAs put their extra blocks on
+    // different pipes (13 blocks: 7, 7, 6, 6 per SM instead of 8, 8, 6, 4; 14 blocks: 7, 7, 7, 7).  Only who computes which columns changes, never the arithmetic of a column.
+    __shared__ int s_jb0[NW], s_nb[NW], s_pipe[NW];
+    const int group_first = (int)blockIdx.y * NW * NB, group_blocks = max(0, min(NW * NB, a.nblk - group_first));
+    int jb0 = group_first + warp * NB;
+    int nbv = max(0, min(NB, a.nblk - jb0));
+    if (NB < 4 && a.tickets != nullptr && group_blocks < NW * NB) {
+        if (lane == 0) {
+            unsigned wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            s_pipe[warp] = (int)(wid & 3u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int ticket = atomicAdd(a.tickets + (smid & 255), 1);
+            int want[4], cap[4] = {0, 0, 0, 0};
+            for (int w = 0; w < NW; ++w) cap[s_pipe[w]] += NB;
+            for (int q = 0; q < 4; ++q) want[q] = group_blocks / 4;
+            const int rem = group_blocks % 4, first = ticket * rem;  // consecutive tickets: consecutive runs of `rem` pipes
+            for (int r = 0; r < rem; ++r) ++want[(first + r) & 3];
+            int left = 0;  // what a pipe cannot take (fewer warps of this CTA on it than on the others) goes where there is room
+            for (int q = 0; q < 4; ++q)
+                if (want[q] > cap[q]) left += want[q] - cap[q], want[q] = cap[q];
+            for (int q = 0; q < 4 && left > 0; ++q) {
+                const int add = min(left, cap[(first + rem + q) & 3] - want[(first + rem + q) & 3]);
+                want[(first + rem + q) & 3] += add, left -= add;
+            }
+            int at = group_first;
+            for (int w = 0; w < NW; ++w) {  // a pipe's share goes to its warps in warp order, NB blocks at most each
+                const int q = s_pipe[w], n = min(NB, want[q]);
+                want[q] -= n;
+                s_jb0[w] = at, s_nb[w] = n;
+                at += n;
+            }
+        }
+        __syncthreads();
+        jb0 = s_jb0[warp], nbv = s_nb[warp];
+    }
     build_table<NW>(a, x, p0, tab);
 
     // ---- main loop -----------------------------------------------------------------------------------------------------
     // The host pads the term list to whole stages of 16 k-steps with zero coefficients and appends two more stages of
     // zeros, so nothing in this loop needs a bounds check: no branch between the DMMAs of a stage.
     const int n_stage = a.k4 / NW;
-    // this warp's output blocks (8 outputs each); block indices are clamped so that every load has a valid address
-    const int jb0 = (blockIdx.y * NW + warp) * NB;
-    const int nbv = max(0, min(NB, a.nblk - jb0));
+    // (block indices are clamped so that every load has a valid address)
     const size_t bstride = (size_t)(a.k4 + kDensePadK4) * 32;
     const double* bbase = a.coef + lane;
     unsigned boff[NB];  // element offsets (the whole matrix has fewer than 2^32 elements: checked at upload)

@@ -89,6 +89,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
         if ((rc = upload(plan.dense_eta0, &dev.dense_eta0, dev.bytes))) return rc;
         if (plan.has_dense) {
             if ((rc = upload(plan.dense_coef, &dev.dense_coef, dev.bytes))) return rc;
+            if ((rc = upload(std::vector<int32_t>(256, 0), &dev.dense_tickets, dev.bytes))) return rc;
             dev.has_dense = true;
         }
     }
@@ -213,7 +214,7 @@ int fast_upload(const FastPlan& plan, FastDevice& dev) {
 
 void fast_free(FastDevice& d) {
     void* ptrs[] = {d.eta, d.tab_pairs, d.tab_factors, d.hot_off, d.hot_pos, d.chunk_dir, d.pipe_dir, d.chunk_meta, d.coef, d.c0,
-                    d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef};
+                    d.nan_off, d.nan_nodes, d.dense_meta, d.dense_eta0, d.dense_coef, d.dense_tickets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     d = FastDevice();
@@ -321,6 +322,7 @@ int run_dense(const FastDevice& d, const double* x, int64_t N, int64_t ldx, doub
     a.n_levels = d.n_levels;
     a.hot_dims = d.hot_dims;
     a.skew = 0;  // (dense_kernel_launch decides)
+    a.tickets = d.dense_tickets;
     for (int l = 0; l < kMaxLevels + 2; ++l) a.level_off[l] = d.level_off[l];
     return dense_kernel_launch(a, x, out, st);
 }
