@@ -83,10 +83,14 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     // partial group is therefore dealt per pipe - floor(blocks / 4) each, the remainder to a run of pipes that starts where
     // the run of the CTA with the previous ticket on this SM ended, so that two resident CTAs put their extra blocks on
     // different pipes (13 blocks: 7, 7, 6, 6 per SM instead of 8, 8, 6, 4; 14 blocks: 7, 7, 7, 7).  Only who computes which columns changes, never the arithmetic of a column.
-    __shared__ int s_jb0[NW], s_nb[NW], s_pipe[NW];
+    // NB = 2 deals HALF blocks (a block for the points 0..15 or 16..31 of the tile: two of the four DMMAs per k-step), so that
+    // the pipes differ by at most half a block: 13 blocks = 26 halves -> 7, 7, 6, 6 per CTA and 13, 13, 13, 13 per SM.  A
+    // warp then has nbv full blocks and possibly one half block (block hblk, half hsel) in its next accumulator slot.
+    __shared__ int s_jb0[NW], s_nb[NW], s_pipe[NW], s_hblk[NW], s_hsel[NW];
     const int group_first = (int)blockIdx.y * NW * NB, group_blocks = max(0, min(NW * NB, a.nblk - group_first));
     int jb0 = group_first + warp * NB;
     int nbv = max(0, min(NB, a.nblk - jb0));
+    int hblk = -1, hsel = 0;
     if (NB < 4 && a.tickets != nullptr && group_blocks < NW * NB) {
         if (lane == 0) {
             unsigned wid;
@@ -114,13 +118,42 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
             for (int w = 0; w < NW; ++w) {  // a pipe's share goes to its warps in warp order, NB blocks at most each
                 const int q = s_pipe[w], n = min(NB, want[q]);
                 want[q] -= n;
-                s_jb0[w] = at, s_nb[w] = n;
+                s_jb0[w] = at, s_nb[w] = n, s_hblk[w] = -1, s_hsel[w] = 0;
                 at += n;
+            }
+            if (NB == 2) {  // the same in halves; kept only if it works out (every half placed, capacities respected)
+                int h[4], fullrem[4], halfrem[4], jb[NW], nb[NW], hb[NW], hs[NW];
+                const int total = 2 * group_blocks, rem_h = total % 4, first_h = ticket * rem_h;
+                bool ok = true;
+                for (int q = 0; q < 4; ++q) h[q] = total / 4;
+                for (int r = 0; r < rem_h; ++r) ++h[(first_h + r) & 3];
+                int n_half = 0, n_full = 0;
+                for (int q = 0; q < 4; ++q) {
+                    ok = ok && h[q] <= 2 * cap[q];
+                    fullrem[q] = h[q] / 2, halfrem[q] = h[q] & 1;
+                    n_full += fullrem[q], n_half += halfrem[q];
+                }
+                ok = ok && (n_half % 2 == 0) && n_full + n_half / 2 == group_blocks;
+                int at_full = group_first, placed = 0;
+                for (int w = 0; w < NW && ok; ++w) {
+                    const int q = s_pipe[w], n = min(NB, fullrem[q]);
+                    fullrem[q] -= n;
+                    jb[w] = at_full, nb[w] = n, hb[w] = -1, hs[w] = 0;
+                    at_full += n;
+                    if (halfrem[q] && n < NB) {  // split blocks are the last ones of the group; their halves alternate
+                        hb[w] = group_first + n_full + placed / 2, hs[w] = placed & 1;
+                        ++placed, halfrem[q] = 0;
+                    }
+                }
+                for (int q = 0; q < 4; ++q) ok = ok && fullrem[q] == 0 && halfrem[q] == 0;
+                if (ok && placed == n_half)
+                    for (int w = 0; w < NW; ++w) s_jb0[w] = jb[w], s_nb[w] = nb[w], s_hblk[w] = hb[w], s_hsel[w] = hs[w];
             }
         }
         __syncthreads();
-        jb0 = s_jb0[warp], nbv = s_nb[warp];
+        jb0 = s_jb0[warp], nbv = s_nb[warp], hblk = s_hblk[warp], hsel = s_hsel[warp];
     }
+    const int nload = nbv + (hblk >= 0 ? 1 : 0);  // accumulator slots in use: full blocks, then the half block
     build_table<NW>(a, x, p0, tab);
 
     // ---- main loop -----------------------------------------------------------------------------------------------------
@@ -132,7 +165,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     const double* bbase = a.coef + lane;
     unsigned boff[NB];  // element offsets (the whole matrix has fewer than 2^32 elements: checked at upload)
 #pragma unroll
-    for (int j = 0; j < NB; ++j) boff[j] = (unsigned)((size_t)min(jb0 + j, a.nblk - 1) * bstride);
+    for (int j = 0; j < NB; ++j) boff[j] = (unsigned)((size_t)(hblk >= 0 && j == nbv ? hblk : min(jb0 + j, a.nblk - 1)) * bstride);
 
     // A assembly: this thread owns (k-step `warp` of the stage, fragment lane `lane`): term 4 * k4 + tig, points gid + 8 i
     const double* xt = x + p0 * a.ldx;  // this tile's rows; row offsets of the lane's four points fit 32 bits
@@ -198,18 +231,26 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
     for (int u = 0; u < PF; ++u)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) bq[u][j] = j < nbv ? __ldg(bbase + boff[j] + u * 32) : 0.0;
+        for (int j = 0; j < NB; ++j) bq[u][j] = j < nload ? __ldg(bbase + boff[j] + u * 32) : 0.0;
 
     // One instantiation per number of blocks the warp really has (the last warp of the last column group has fewer than NB):
     // a DMMA that is predicated off still occupies the FP64 pipe for its 16 cycles (profiles/r06_k1_experiments.md, r08), so
     // "j < nbv" must be resolved at compile time, not by a predicate.
-    auto stage_mma = [&](int s, auto nb_tag) {
+    auto stage_mma = [&](int s, auto nb_tag, auto half_tag) {
         constexpr int NBV = decltype(nb_tag)::value;
+        constexpr bool HALF = decltype(half_tag)::value;  // one more block in slot NBV, for two of the four point groups
         const double2* af = reinterpret_cast<const double2*>(abuf + (s & 1) * NW * 128) + lane;
         const double* bp = bbase + (size_t)s * NW * 32;
 #pragma unroll
         for (int kk = 0; kk < NW; ++kk) {
             const double2 a01 = af[kk * 64], a23 = af[kk * 64 + 32];
+            if (HALF) {
+                constexpr int JH = NBV < NB ? NBV : NB - 1;
+                const double2 ah = hsel ? a23 : a01;
+                dmma(acc[0][JH], ah.x, bq[kk % PF][JH]);
+                dmma(acc[1][JH], ah.y, bq[kk % PF][JH]);
+                bq[kk % PF][JH] = __ldg(bp + boff[JH] + (kk + PF) * 32);
+            }
 #pragma unroll
             for (int j = 0; j < NBV; ++j) {
                 dmma(acc[0][j], a01.x, bq[kk % PF][j]);
@@ -227,8 +268,10 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     // its only partial warp is the last one of the last of many column groups: that one multiplies its clamped duplicate blocks
     // too and drops them in the epilogue)
     auto stage_mma_any = [&](int s) {
-        if (nbv == NB || (NB == 4 && nbv > 0)) stage_mma(s, std::integral_constant<int, NB>());
-        else if (NB == 2 && nbv == 1) stage_mma(s, std::integral_constant<int, 1>());
+        if (nbv == NB || (NB == 4 && nbv > 0)) stage_mma(s, std::integral_constant<int, NB>(), std::false_type());
+        else if (NB == 2 && nbv == 1 && hblk < 0) stage_mma(s, std::integral_constant<int, 1>(), std::false_type());
+        else if (NB == 2 && nbv == 1) stage_mma(s, std::integral_constant<int, 1>(), std::true_type());
+        else if (NB == 2 && hblk >= 0) stage_mma(s, std::integral_constant<int, 0>(), std::true_type());
     };
     static_assert(NB == 1 || NB == 2 || NB == 4, "partial warps: NB = 2 has its own instantiation, NB = 4 clamps (below)");
 
@@ -251,15 +294,17 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     const bool vec = a.colmap == nullptr && (a.ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-        if (j >= nbv) break;
-        const long long col = 8ll * (jb0 + j) + 2 * tig;
+        if (j >= nload) break;
+        const bool is_half = j >= nbv;  // accumulators 0, 1 of the slot hold point groups 2 hsel, 2 hsel + 1
+        const long long col = 8ll * (is_half ? hblk : jb0 + j) + 2 * tig;
         if (col >= a.ncol) continue;
         const bool two = col + 1 < a.ncol;
         const double c0a = __ldg(a.c0 + col), c0b = two ? __ldg(a.c0 + col + 1) : 0.0;
         const long long ya = a.colmap ? __ldg(a.colmap + col) : col, yb = a.colmap && two ? __ldg(a.colmap + col + 1) : col + 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const long long p = p0 + gid + 8 * i;
+            if (is_half && i >= 2) break;
+            const long long p = p0 + gid + 8 * (is_half ? 2 * hsel + i : i);
             if (p >= a.N) continue;
             double* dst = y + p * a.ldy;
             if (vec) {
