@@ -86,12 +86,15 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     // NB = 2 deals HALF blocks (a block for the points 0..15 or 16..31 of the tile: two of the four DMMAs per k-step), so that
     // the pipes differ by at most half a block: 13 blocks = 26 halves -> 7, 7, 6, 6 per CTA and 13, 13, 13, 13 per SM.  A
     // warp then has nbv full blocks and possibly one half block (block hblk, half hsel) in its next accumulator slot.
-    __shared__ int s_jb0[NW], s_nb[NW], s_pipe[NW], s_hblk[NW], s_hsel[NW];
+    int jb0 = 0, nbv = 0, hblk = -1, hsel = 0;
+    // (compiled out of the four-block shape, which is at its register limit: its partial group is one of many, and these
+    // values alive across the table build cost it 2 % - cfg3 584 -> 596 ms; it takes its blocks in warp order, below)
+    if constexpr (NB < 4) {
     const int group_first = (int)blockIdx.y * NW * NB, group_blocks = max(0, min(NW * NB, a.nblk - group_first));
-    int jb0 = group_first + warp * NB;
-    int nbv = max(0, min(NB, a.nblk - jb0));
-    int hblk = -1, hsel = 0;
-    if (NB < 4 && a.tickets != nullptr && group_blocks < NW * NB) {
+    jb0 = group_first + warp * NB;
+    nbv = max(0, min(NB, a.nblk - jb0));
+    __shared__ int s_jb0[NW], s_nb[NW], s_pipe[NW], s_hblk[NW], s_hsel[NW];
+    if (a.tickets != nullptr && group_blocks < NW * NB) {
         if (lane == 0) {
             unsigned wid;
             asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
@@ -153,8 +156,13 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
         __syncthreads();
         jb0 = s_jb0[warp], nbv = s_nb[warp], hblk = s_hblk[warp], hsel = s_hsel[warp];
     }
-    const int nload = nbv + (hblk >= 0 ? 1 : 0);  // accumulator slots in use: full blocks, then the half block
+    }
     build_table<NW>(a, x, p0, tab);
+    if constexpr (NB == 4) {
+        jb0 = (blockIdx.y * NW + warp) * NB;
+        nbv = max(0, min(NB, a.nblk - jb0));
+    }
+    const int nload = NB < 4 ? nbv + (hblk >= 0 ? 1 : 0) : nbv;  // accumulator slots in use: full blocks, then the half block
 
     // ---- main loop -----------------------------------------------------------------------------------------------------
     // The host pads the term list to whole stages of 16 k-steps with zero coefficients and appends two more stages of
@@ -165,7 +173,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     const double* bbase = a.coef + lane;
     unsigned boff[NB];  // element offsets (the whole matrix has fewer than 2^32 elements: checked at upload)
 #pragma unroll
-    for (int j = 0; j < NB; ++j) boff[j] = (unsigned)((size_t)(hblk >= 0 && j == nbv ? hblk : min(jb0 + j, a.nblk - 1)) * bstride);
+    for (int j = 0; j < NB; ++j) boff[j] = (unsigned)((size_t)(NB < 4 && hblk >= 0 && j == nbv ? hblk : min(jb0 + j, a.nblk - 1)) * bstride);
 
     // A assembly: this thread owns (k-step `warp` of the stage, fragment lane `lane`): term 4 * k4 + tig, points gid + 8 i
     const double* xt = x + p0 * a.ldx;  // this tile's rows; row offsets of the lane's four points fit 32 bits
@@ -295,7 +303,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
         if (j >= nload) break;
-        const bool is_half = j >= nbv;  // accumulators 0, 1 of the slot hold point groups 2 hsel, 2 hsel + 1
+        const bool is_half = NB < 4 && j >= nbv;  // accumulators 0, 1 of the slot hold point groups 2 hsel, 2 hsel + 1
         const long long col = 8ll * (is_half ? hblk : jb0 + j) + 2 * tig;
         if (col >= a.ncol) continue;
         const bool two = col + 1 < a.ncol;
