@@ -379,7 +379,6 @@ def cfg5_sweep(args, world, rank, local, peaks):
     wl = workloads.CONFIGS["cfg5"]
     total = args.sweep_points
     chunk = min(500_000, total)  # 200 chunks at the default total: the same number of chunks per rank at 1, 2, 4 and 8 GPUs
-    n_chunks = (total + chunk - 1) // chunk
     ip = SmolyakBarycentricInterpolator(node_gen=wl.generator(), k=wl.k(), t=wl.threshold(), d_out=wl.d_out, device=local, batched_f=True)
     layout = ip._assemble(wl.target(), {})[0] if rank == 0 else None
     layout = sdist.broadcast_layout(layout, src=0)
@@ -395,8 +394,7 @@ def cfg5_sweep(args, world, rank, local, peaks):
     torch.cuda.synchronize()
     ms, points, checksum = 0.0, 0, 0.0
     t_wall = time.perf_counter()
-    for c in range(rank, n_chunks, world):
-        n = min(chunk, total - c * chunk)
+    for c, _, n in sdist.shard_chunks(total, chunk, rank, world):
         gen.manual_seed(977 * 1_000_003 + c)
         x.uniform_(-1, 1, generator=gen)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

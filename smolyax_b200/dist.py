@@ -21,6 +21,17 @@ def shard_rows(n_rows: int, rank: int, world: int):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def shard_chunks(n_total: int, chunk: int, rank: int, world: int):
+    """Chunks of a long sweep dealt round-robin: yields ``(chunk index, first point, points)`` of this rank's chunks of
+    ``range(n_total)`` cut into pieces of ``chunk`` points (the last one may be shorter).  Chunk ``c`` is the same set of points
+    at every world size, so a generator keyed by the chunk index produces the same inputs on 1, 2, 4 or 8 GPUs
+    (``bench.py``: the 10^8-point sweep of BASELINE's configs[4])."""
+    n_chunks = (int(n_total) + int(chunk) - 1) // int(chunk)
+    for c in range(int(rank), n_chunks, int(world)):
+        first = c * int(chunk)
+        yield c, first, min(int(chunk), int(n_total) - first)
+
+
 def _device_for_backend():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 

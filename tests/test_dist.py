@@ -21,6 +21,23 @@ def test_shard_rows_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_chunks_cover_every_point_once_at_every_world_size():
+    for total, chunk in ((100_000_000, 500_000), (1_000_003, 4096), (5, 7), (0, 10)):
+        for world in (1, 2, 4, 8):
+            seen = []
+            per_rank = []
+            for r in range(world):
+                mine = list(sdist.shard_chunks(total, chunk, r, world))
+                per_rank.append(sum(n for _, _, n in mine))
+                seen += mine
+            seen.sort()
+            assert [c for c, _, _ in seen] == list(range((total + chunk - 1) // chunk))  # every chunk exactly once
+            assert all(first == c * chunk and 0 < n <= chunk for c, first, n in seen)
+            assert sum(per_rank) == total
+            if total == 100_000_000:  # the sweep of bench.py: the same number of points on every rank at 1, 2, 4 and 8 GPUs
+                assert len(set(per_rank)) == 1
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
