@@ -109,7 +109,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     digest = source_hash(srcs + headers, flags)
     stamp = read_stamp(CUDA_LIB)
     if not force and CUDA_LIB.exists() and stamp.get("source_hash") == digest:
-        LAST_BUILD[CUDA_LIB.name] = "reused (source hash matches)"
+        LAST_BUILD.setdefault(CUDA_LIB.name, "reused (source hash matches)")  # (a rebuild earlier in this process stays on record)
         return CUDA_LIB
     nvcc = nvcc_path()
     if nvcc is None:
