@@ -185,9 +185,10 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
     // the subtraction happens in assemble, a stage later.  Written as "xc = ldg(..) - e0" the compiler put the DADD right behind
     // the loads, in front of the stage's DMMAs, and every warp waited there for L2 once per stage (ncu r08: 9 % of all samples
     // on those DADDs with long-scoreboard stalls).  Measured r08, ms: cfg3 at full size (16 warps x 4 blocks) 616 -> 584, split-K
-    // kernel at cfg4's tables and 16 outputs 2.89 -> 2.76; the skewed 8-warp shapes LOSE 2.5 % (cfg5 77.1 -> 79.1) and keep
-    // the subtraction at the load.
-    constexpr bool kLateSub = NB == 4;
+    // kernel at cfg4's tables and 16 outputs 2.89 -> 2.76; the skewed 8-warp shapes first lost 2.5 % with it (cfg5 77.1 ->
+    // 79.1: the extra DADD lengthened the assembly chain in front of the stage barrier while the fullest FP64 pipe set the pace)
+    // and gain 1.3 % since their blocks are dealt per pipe (cfg5 68.85 -> 67.98).
+    constexpr bool kLateSub = true;  // (r08, after the per-pipe dealing: also the narrow shapes gain, cfg5 68.85 -> 67.98 ms; before it they lost 2.5 %)
     double xc[4] = {0.0, 0.0, 0.0, 0.0}, xe0 = 0.0;
     auto load_cold = [&](int2 m) {
         if (m.y < 0) {
