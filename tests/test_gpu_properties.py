@@ -279,6 +279,26 @@ def test_block_sparse_kernel_small_batches_many_outputs_and_knobs():
     assert np.allclose(ip_c(xc), fp(xc), rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("d_out", [72, 100, 203])
+def test_dense_kernel_block_dealing_never_changes_a_bit(d_out):
+    """The staged dense kernel deals the output blocks of a column group that does not fill the CTA to its warps per FP64 pipe
+    (%warpid), in half blocks, rotated by a per-SM ticket that advances with every CTA - so consecutive launches compute the
+    same columns on different warps.  Only who computes a column may change, never its arithmetic: many launches, batch sizes
+    with ragged last tiles, all bit-identical; and equal to the block-sparse kernels within the usual bound."""
+    w = workloads.Workload("deal", "leja", 40, d_out, 600, 0)
+    ip = _interp(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(), batched_f=True, dense=True)
+    assert ip.device_info()["has_dense_path"] == 1
+    x = torch.from_numpy(w.points(3000, seed=7)).cuda()
+    y0 = ip(x)
+    for _ in range(6):
+        assert torch.equal(ip(x), y0)
+    for n in (1, 33, 1000, 2999):
+        assert torch.equal(ip(x[:n]), y0[:n])
+    sparse = _interp(node_gen=w.generator(), k=w.k(), t=w.threshold(), d_out=d_out, f=w.target(), batched_f=True, dense=False)
+    scale = float(y0.abs().max())
+    assert float((sparse(x[:256]) - y0[:256]).abs().max()) <= 1e-12 * max(1.0, scale) * 50
+
+
 def test_out_buffer_of_each_input_kind():
     """``__call__(x, out=...)``: the caller's result buffer (device, page-locked host, NumPy) receives the same bits as a
     fresh one; a buffer of the wrong shape, type or kind is refused like any other bad argument (AssertionError)."""
