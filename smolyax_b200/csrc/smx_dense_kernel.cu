@@ -105,53 +105,7 @@ dense_eval_kernel(const DenseArgs a, const double* __restrict__ x, double* __res
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             const int ticket = atomicAdd(a.tickets + (smid & 255), 1);
-            int want[4], cap[4] = {0, 0, 0, 0};
-            for (int w = 0; w < NW; ++w) cap[s_pipe[w]] += NB;
-            for (int q = 0; q < 4; ++q) want[q] = group_blocks / 4;
-            const int rem = group_blocks % 4, first = ticket * rem;  // consecutive tickets: consecutive runs of `rem` pipes
-            for (int r = 0; r < rem; ++r) ++want[(first + r) & 3];
-            int left = 0;  // what a pipe cannot take (fewer warps of this CTA on it than on the others) goes where there is room
-            for (int q = 0; q < 4; ++q)
-                if (want[q] > cap[q]) left += want[q] - cap[q], want[q] = cap[q];
-            for (int q = 0; q < 4 && left > 0; ++q) {
-                const int add = min(left, cap[(first + rem + q) & 3] - want[(first + rem + q) & 3]);
-                want[(first + rem + q) & 3] += add, left -= add;
-            }
-            int at = group_first;
-            for (int w = 0; w < NW; ++w) {  // a pipe's share goes to its warps in warp order, NB blocks at most each
-                const int q = s_pipe[w], n = min(NB, want[q]);
-                want[q] -= n;
-                s_jb0[w] = at, s_nb[w] = n, s_hblk[w] = -1, s_hsel[w] = 0;
-                at += n;
-            }
-            if (NB == 2) {  // the same in halves; kept only if it works out (every half placed, capacities respected)
-                int h[4], fullrem[4], halfrem[4], jb[NW], nb[NW], hb[NW], hs[NW];
-                const int total = 2 * group_blocks, rem_h = total % 4, first_h = ticket * rem_h;
-                bool ok = true;
-                for (int q = 0; q < 4; ++q) h[q] = total / 4;
-                for (int r = 0; r < rem_h; ++r) ++h[(first_h + r) & 3];
-                int n_half = 0, n_full = 0;
-                for (int q = 0; q < 4; ++q) {
-                    ok = ok && h[q] <= 2 * cap[q];
-                    fullrem[q] = h[q] / 2, halfrem[q] = h[q] & 1;
-                    n_full += fullrem[q], n_half += halfrem[q];
-                }
-                ok = ok && (n_half % 2 == 0) && n_full + n_half / 2 == group_blocks;
-                int at_full = group_first, placed = 0;
-                for (int w = 0; w < NW && ok; ++w) {
-                    const int q = s_pipe[w], n = min(NB, fullrem[q]);
-                    fullrem[q] -= n;
-                    jb[w] = at_full, nb[w] = n, hb[w] = -1, hs[w] = 0;
-                    at_full += n;
-                    if (halfrem[q] && n < NB) {  // split blocks are the last ones of the group; their halves alternate
-                        hb[w] = group_first + n_full + placed / 2, hs[w] = placed & 1;
-                        ++placed, halfrem[q] = 0;
-                    }
-                }
-                for (int q = 0; q < 4; ++q) ok = ok && fullrem[q] == 0 && halfrem[q] == 0;
-                if (ok && placed == n_half)
-                    for (int w = 0; w < NW; ++w) s_jb0[w] = jb[w], s_nb[w] = nb[w], s_hblk[w] = hb[w], s_hsel[w] = hs[w];
-            }
+            deal_blocks(NW, NB, s_pipe, group_first, group_blocks, ticket, s_jb0, s_nb, s_hblk, s_hsel);  // (smx_plan.h)
         }
         __syncthreads();
         jb0 = s_jb0[warp], nbv = s_nb[warp], hblk = s_hblk[warp], hsel = s_hsel[warp];

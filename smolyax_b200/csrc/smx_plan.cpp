@@ -1389,6 +1389,10 @@ void smxh_plan_stats(void* p, int64_t* out) {
     std::memcpy(out, v, sizeof(v));
 }
 void smxh_plan_bank_stats(void* p, int64_t* out) { std::memcpy(out, static_cast<smx::FastPlan*>(p)->bank_stats, 6 * sizeof(int64_t)); }
+// (test hook) deal_blocks of smx_plan.h: out = jb0[nw], nbv[nw], hblk[nw], hsel[nw]
+void smxh_deal_blocks(int32_t nw, int32_t nb, const int32_t* pipe, int32_t group_first, int32_t group_blocks, int32_t ticket, int32_t* out) {
+    smx::deal_blocks(nw, nb, pipe, group_first, group_blocks, ticket, out, out + nw, out + 2 * nw, out + 3 * nw);
+}
 // gradient jobs: out = [n_jobs, n_items, k-steps of all items, cold jobs, most items of a job, most k-steps of a job, zero ranges]
 void smxh_plan_grad_stats(void* p, int64_t* out) {
     auto* pl = static_cast<smx::FastPlan*>(p);

@@ -207,6 +207,67 @@ struct PlanOptions {
     bool dense_if_cheaper = false;
 };
 
+// ---- staged dense kernel: which output blocks a warp of the CTA multiplies (smx_dense_kernel.cu) --------------------------------
+// A column group of `group_blocks` blocks (8 outputs each) that does not fill the CTA (nw warps x nb blocks) is dealt per FP64
+// pipe: pipe[w] = %warpid & 3 of warp w.  Every pipe gets floor(units / 4) units, the remainder goes to a run of pipes that
+// starts at ticket * remainder (consecutive tickets of one SM continue where the previous CTA stopped); unit = a block, or - for
+// nb = 2 - half a block (the points 0..15 or 16..31 of the tile).  Warp w then has nbv[w] full blocks jb0[w] .. and, if
+// hblk[w] >= 0, half hsel[w] of block hblk[w].  Every block of the group is covered exactly once whatever the placement of the
+// warps (tests/test_plan.py runs this function on the host over all group sizes, tickets and placements).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void deal_blocks(int nw, int nb, const int* pipe, int group_first, int group_blocks, int ticket, int* jb0, int* nbv, int* hblk,
+                        int* hsel) {
+    int want[4], cap[4] = {0, 0, 0, 0};
+    for (int w = 0; w < nw; ++w) cap[pipe[w] & 3] += nb;
+    for (int q = 0; q < 4; ++q) want[q] = group_blocks / 4;
+    const int rem = group_blocks % 4, first = ticket * rem;
+    for (int r = 0; r < rem; ++r) ++want[(first + r) & 3];
+    int left = 0;  // what a pipe cannot take (fewer warps of this CTA on it than on the others) goes where there is room
+    for (int q = 0; q < 4; ++q)
+        if (want[q] > cap[q]) left += want[q] - cap[q], want[q] = cap[q];
+    for (int q = 0; q < 4 && left > 0; ++q) {
+        const int t = (first + rem + q) & 3, room = cap[t] - want[t], add = left < room ? left : room;
+        want[t] += add, left -= add;
+    }
+    int at = group_first;
+    for (int w = 0; w < nw; ++w) {  // a pipe's share goes to its warps in warp order, nb blocks at most each
+        const int q = pipe[w] & 3, n = nb < want[q] ? nb : want[q];
+        want[q] -= n;
+        jb0[w] = at, nbv[w] = n, hblk[w] = -1, hsel[w] = 0;
+        at += n;
+    }
+    if (nb != 2 || nw > 16) return;
+    // the same in halves; kept only if it works out (every half placed, capacities respected)
+    int h[4], fullrem[4], halfrem[4], jb[16], nn[16], hb[16], hs[16];
+    const int total = 2 * group_blocks, rem_h = total % 4, first_h = ticket * rem_h;
+    bool ok = true;
+    for (int q = 0; q < 4; ++q) h[q] = total / 4;
+    for (int r = 0; r < rem_h; ++r) ++h[(first_h + r) & 3];
+    int n_half = 0, n_full = 0;
+    for (int q = 0; q < 4; ++q) {
+        ok = ok && h[q] <= 2 * cap[q];
+        fullrem[q] = h[q] / 2, halfrem[q] = h[q] & 1;
+        n_full += fullrem[q], n_half += halfrem[q];
+    }
+    ok = ok && (n_half % 2 == 0) && n_full + n_half / 2 == group_blocks;
+    int at_full = group_first, placed = 0;
+    for (int w = 0; w < nw && ok; ++w) {
+        const int q = pipe[w] & 3, n = nb < fullrem[q] ? nb : fullrem[q];
+        fullrem[q] -= n;
+        jb[w] = at_full, nn[w] = n, hb[w] = -1, hs[w] = 0;
+        at_full += n;
+        if (halfrem[q] && n < nb) {  // split blocks are the last ones of the group; their halves alternate
+            hb[w] = group_first + n_full + placed / 2, hs[w] = placed & 1;
+            ++placed, halfrem[q] = 0;
+        }
+    }
+    for (int q = 0; q < 4; ++q) ok = ok && fullrem[q] == 0 && halfrem[q] == 0;
+    if (ok && placed == n_half)
+        for (int w = 0; w < nw; ++w) jb0[w] = jb[w], nbv[w] = nn[w], hblk[w] = hb[w], hsel[w] = hs[w];
+}
+
 // value-table row (minus one) of hot entry h
 #ifdef __CUDACC__
 __host__ __device__

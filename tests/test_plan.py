@@ -236,6 +236,52 @@ def test_compact_layout_gives_the_same_plan(case):
     np.testing.assert_allclose(q, g["Q_ref"], rtol=2e-9, atol=2e-9)  # the reference's own summation noise (test_oracle.py)
 
 
+def test_dense_kernel_block_dealing_covers_every_block_exactly_once():
+    """smx_plan.h::deal_blocks (run by thread 0 of every CTA of the staged dense kernel): for every CTA shape, group size, ticket
+    and placement of the warps on the four FP64 pipes - the regular rotations the hardware uses and arbitrary ones - every
+    block of the group is multiplied exactly once (as a whole, or as two halves on two warps), no warp gets more than its
+    accumulators hold, and with a regular placement the pipes differ by at most one unit (half a block for two-block warps),
+    consecutive tickets putting their extra units on different pipes."""
+    _host.smxh_deal_blocks.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    _host.smxh_deal_blocks.restype = None
+    rng = np.random.default_rng(5)
+
+    def deal(nw, nb, pipe, first, blocks, ticket):
+        pipe = np.ascontiguousarray(pipe, dtype=np.int32)
+        out = np.full(4 * nw, -7, dtype=np.int32)
+        _host.smxh_deal_blocks(nw, nb, pipe.ctypes.data, first, blocks, ticket, out.ctypes.data)
+        return out.reshape(4, nw)
+
+    for nw, nb in ((8, 2), (8, 1), (16, 1), (16, 2)):
+        placements = [[(w + r) % 4 for w in range(nw)] for r in range(4)]
+        placements += [rng.integers(0, 4, nw).tolist() for _ in range(12)] + [[0] * nw, [1] * (nw - 1) + [3]]
+        for pi, pipe in enumerate(placements):
+            regular = pi < 4
+            for blocks in range(1, nw * nb):
+                loads_by_ticket = []
+                for ticket in (0, 1, 2, 3, 5, -1, 2**31 - 1):
+                    first = 16 * (ticket & 3)
+                    jb0, nbv, hblk, hsel = deal(nw, nb, pipe, first, blocks, ticket)
+                    cover = np.zeros((blocks, 2), dtype=int)  # halves of every block of the group
+                    load = np.zeros(4, dtype=int)             # units of half a block per pipe
+                    for w in range(nw):
+                        assert 0 <= nbv[w] <= nb and nbv[w] + (hblk[w] >= 0) <= nb
+                        for j in range(nbv[w]):
+                            cover[jb0[w] + j - first] += 1
+                        load[pipe[w]] += 2 * nbv[w]
+                        if hblk[w] >= 0:
+                            assert nb == 2 and hsel[w] in (0, 1)
+                            cover[hblk[w] - first, hsel[w]] += 1
+                            load[pipe[w]] += 1
+                    assert (cover == 1).all(), (nw, nb, pipe, blocks, ticket, cover.T)
+                    if regular:
+                        unit = 1 if nb == 2 else 2
+                        assert load.max() - load.min() <= unit, (nw, nb, pipe, blocks, ticket, load)
+                    loads_by_ticket.append(load)
+                if regular and nb == 2 and blocks % 2 == 1:  # 26 halves: two tickets in a row level the SM
+                    assert (loads_by_ticket[0] + loads_by_ticket[1]).max() - (loads_by_ticket[0] + loads_by_ticket[1]).min() == 0
+
+
 def test_compact_descriptor_offsets_must_start_at_zero():
     """The compact descriptor carries no array lengths: an offset array shifted as a whole passes every per-summand difference
     check and would read past the end of val_index / dims (a GPU negative test was flaky on exactly that before the plan
